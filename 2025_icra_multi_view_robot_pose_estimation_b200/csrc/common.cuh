@@ -1,0 +1,176 @@
+// common.cuh — device helpers shared by the mvgeo kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "mvgeo.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "mvgeo kernels are written for sm_100a (B200); build with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+#define MVGEO_CHECK_LAUNCH()                          \
+  do {                                                \
+    cudaError_t e__ = cudaGetLastError();             \
+    if (e__ != cudaSuccess) return (int)e__;          \
+  } while (0)
+
+#define MVGEO_CUDA(call)                              \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return (int)e__;          \
+  } while (0)
+
+namespace mvgeo {
+
+constexpr float kLog2e = 1.4426950408889634f;
+// Soft-arg-max skip threshold (natural-log units): elements whose weight relative to the
+// peak is below exp(-kSoftSkip) = 1.3e-14 are not accumulated (worst-case centroid error
+// n_pixels * W * 1.3e-14 < 3e-6 px at 480x640).
+constexpr float kSoftSkip = 32.0f;
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float max_nan_f32(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t max_nan_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t max_nan_f16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// (value, index) ordering of torch.argmax: larger value wins, NaN is maximal, ties (equal
+// values, -0 == +0, or two NaNs) go to the lower index. True when (v2,i2) beats (v1,i1).
+__device__ __forceinline__ bool argmax_better(float v1, int i1, float v2, int i2) {
+  const bool n1 = (v1 != v1), n2 = (v2 != v2);
+  if (n1 != n2) return n2;
+  if (!n1) {
+    if (v2 > v1) return true;
+    if (v2 < v1) return false;
+  }
+  return i2 < i1;
+}
+
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, off);
+    if (argmax_better(v, i, ov, oi)) {
+      v = ov;
+      i = oi;
+    }
+  }
+}
+
+// Fixed-order (deterministic) warp sum.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Element access for the three belief-map dtypes. A "chunk" is one 16-byte vector.
+template <int DT> struct Elem;
+
+template <> struct Elem<MVGEO_F32> {
+  static constexpr int kBytes = 4;
+  static constexpr int kPerChunk = 4;
+  using carrier = float;  // how a chunk maximum is kept in shared memory
+  __device__ static __forceinline__ float chunk_max(const uint4& c) {
+    return max_nan_f32(max_nan_f32(__uint_as_float(c.x), __uint_as_float(c.y)),
+                       max_nan_f32(__uint_as_float(c.z), __uint_as_float(c.w)));
+  }
+  __device__ static __forceinline__ float get(const uint4& c, int j) {
+    const uint32_t w = j == 0 ? c.x : j == 1 ? c.y : j == 2 ? c.z : c.w;
+    return __uint_as_float(w);
+  }
+  __device__ static __forceinline__ carrier pack(float m) { return m; }
+  __device__ static __forceinline__ float unpack(carrier m) { return m; }
+  __device__ static __forceinline__ float load(const void* base, int64_t i) {
+    return __ldg(reinterpret_cast<const float*>(base) + i);
+  }
+  __device__ static __forceinline__ void store(void* base, int64_t i, float v) {
+    reinterpret_cast<float*>(base)[i] = v;
+  }
+  __device__ static __forceinline__ uint4 neg_inf_chunk() {
+    return make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+  }
+};
+
+template <> struct Elem<MVGEO_BF16> {
+  static constexpr int kBytes = 2;
+  static constexpr int kPerChunk = 8;
+  using carrier = uint16_t;
+  __device__ static __forceinline__ float chunk_max(const uint4& c) {
+    const uint32_t m = max_nan_bf16x2(max_nan_bf16x2(c.x, c.y), max_nan_bf16x2(c.z, c.w));
+    return max_nan_f32(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+  }
+  __device__ static __forceinline__ float get(const uint4& c, int j) {
+    const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
+    return __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  __device__ static __forceinline__ carrier pack(float m) { return (uint16_t)(__float_as_uint(m) >> 16); }
+  __device__ static __forceinline__ float unpack(carrier m) { return __uint_as_float(((uint32_t)m) << 16); }
+  __device__ static __forceinline__ float load(const void* base, int64_t i) {
+    return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + i)) << 16);
+  }
+  __device__ static __forceinline__ void store(void* base, int64_t i, float v) {
+    reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  }
+  __device__ static __forceinline__ uint4 neg_inf_chunk() {
+    return make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+  }
+};
+
+template <> struct Elem<MVGEO_F16> {
+  static constexpr int kBytes = 2;
+  static constexpr int kPerChunk = 8;
+  using carrier = uint16_t;
+  __device__ static __forceinline__ float h2f(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+  __device__ static __forceinline__ float chunk_max(const uint4& c) {
+    const uint32_t m = max_nan_f16x2(max_nan_f16x2(c.x, c.y), max_nan_f16x2(c.z, c.w));
+    return max_nan_f32(h2f((uint16_t)(m & 0xffffu)), h2f((uint16_t)(m >> 16)));
+  }
+  __device__ static __forceinline__ float get(const uint4& c, int j) {
+    const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
+    return h2f((uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu)));
+  }
+  // every half is exactly representable in float and the maximum IS one of the inputs,
+  // so the round trip through __float2half_rn is exact
+  __device__ static __forceinline__ carrier pack(float m) { return __half_as_ushort(__float2half_rn(m)); }
+  __device__ static __forceinline__ float unpack(carrier m) { return h2f(m); }
+  __device__ static __forceinline__ float load(const void* base, int64_t i) {
+    return h2f(__ldg(reinterpret_cast<const uint16_t*>(base) + i));
+  }
+  __device__ static __forceinline__ void store(void* base, int64_t i, float v) {
+    reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+  }
+  __device__ static __forceinline__ uint4 neg_inf_chunk() {
+    return make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+  }
+};
+
+}  // namespace mvgeo

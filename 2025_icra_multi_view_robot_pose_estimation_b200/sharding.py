@@ -1,0 +1,48 @@
+"""Frame sharding across the GPUs of one box.
+
+Frames are independent in every kernel of the path, so rank r simply owns a contiguous block
+of frames — the same partition the reference gets from DistributedSampler
+(model/MvRoPose_FR3.py:946) — and there is NO collective inside decode -> triangulate -> FK.
+The only communication is the final result gather (NCCL all_gather over NVLink; gloo in the
+CPU tests), < 1 KB per frame.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def frame_range(n_frames: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block [begin, end) of rank `rank`; the remainder goes to the LAST ranks."""
+    if world_size < 1 or not (0 <= rank < world_size) or n_frames < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n_frames, world_size)
+    first_big = world_size - rem  # ranks >= first_big get base + 1 frames
+    begin = rank * base + max(0, rank - first_big)
+    return begin, begin + base + (1 if rank >= first_big else 0)
+
+
+def gather_frames(local: Dict[str, torch.Tensor], n_frames: int, group=None) -> Dict[str, torch.Tensor]:
+    """All-gather per-frame result tensors (leading dimension = this rank's frames, in
+    frame_range order) into full tensors of leading dimension n_frames on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(local)
+    ws, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = [frame_range(n_frames, r, ws)[1] - frame_range(n_frames, r, ws)[0] for r in range(ws)]
+    cap = max(counts)
+    out = {}
+    for name, t in local.items():
+        if t.dim() == 0:
+            continue
+        if t.shape[0] != counts[rank]:
+            raise ValueError(f"{name}: leading dimension {t.shape[0]} != this rank's {counts[rank]} frames")
+        pad = t
+        if counts[rank] < cap:  # equal-sized contributions: one all_gather_into_tensor
+            pad = torch.cat([t, t.new_zeros((cap - counts[rank],) + tuple(t.shape[1:]))], dim=0)
+        buf = pad.new_empty((ws * cap,) + tuple(t.shape[1:]))
+        dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+        parts = [buf[r * cap: r * cap + counts[r]] for r in range(ws)]
+        out[name] = torch.cat(parts, dim=0) if any(c != cap for c in counts) else buf
+    return out

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of decode + triangulate + FK on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # N > 1: one rank per GPU, weak scaling
+
+Workload (config 2 of BASELINE.json): FR3, 4 views, 1024 frames per GPU per step, 8 key-points,
+240x320 bf16 belief maps = 5.03 GB per step per GPU (>> 126 MB L2, so no flush is needed
+between steps). Synthetic closed-loop data: joint angles -> FK -> projection -> Gaussian blobs
+(sigma 3 px) + N(0, 0.01) noise, generated on the device before the timed region.
+
+A step = one pass of the hot path over one batch: belief-map decode (arg-max + global
+soft-arg-max) -> DLT triangulation -> FK + reprojection consistency, then (N > 1) the final
+NCCL result gather. `value` times K steps with CUDA events on the launching stream, inputs
+resident in HBM; `e2e` times the host-buffer C-ABI call (pinned host maps in, host results
+out, H2D/D2H inside the timed region). `roofline` is the decode kernel: algorithmic bytes
+(V*K*H*W*2 per frame) over its CUDA-event duration inside the same timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ROBOT, V, B, H, W = "fr3", 4, 1024, 240, 320
+BETA, MIN_SCORE = 100.0, 0.5
+METRIC = "frames/s decode+triangulate+FK"
+WORKLOAD = f"C2: FR3 {V}-view, batch {B} frames/GPU, {H}x{W} bf16 belief maps, decode+triangulate+FK"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _intrinsics():
+    import mvgeo
+
+    return [[[v[0], 0.0, v[2]], [0.0, v[1], v[3]], [0.0, 0.0, 1.0]] for v in mvgeo.ZEDX_FHD1200.values()]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port; the reference itself is
+    Python and cannot travel to the GPU box), all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_pipeline as cp
+
+    ncores = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        per_step = max(2.0, min(10.0, 90.0 / max(1, args.warmup + args.steps)))
+        fps, workers, total, desc = cp.timed_throughput(ROBOT, V, H, W, (1200, 1920), _intrinsics(), frames_per_worker=4,
+                                                        min_seconds=per_step, workers=ncores)
+        if i >= args.warmup:
+            vals.append(fps)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * B / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU path; ms_per_step = time for one 1024-frame batch at the measured rate"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_inputs(mv, torch, dev, rank):
+    """Closed-loop synthetic belief maps on the device (untimed)."""
+    import numpy as np
+
+    chain = mv.Chain.builtin(ROBOT)
+    rig = mv.CameraRig.synthetic_ring(V)
+    Rv = np.stack([np.asarray(mv.view_rotation(ROBOT, f"view{v + 1}")) for v in range(V)]).astype(np.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    q = (torch.rand((B, chain.n_joints), generator=g, device=dev) * 2.0 - 1.0) * (0.9 * 2.8)
+    X = mv.forward_kinematics(chain, q, Rv)
+    uv = mv.project_points(X, rig)
+    Hi, Wi = rig.image_size
+    kp_map = uv * torch.tensor([W / Wi, H / Hi], device=dev)
+    maps = mv.encode_gaussian(kp_map, (H, W), 3.0, torch.bfloat16)
+    for b0 in range(0, B, 64):  # noise in slices: no 10 GB temporary
+        sl = maps[b0:b0 + 64]
+        sl.add_(torch.randn(sl.shape, generator=g, device=dev, dtype=torch.float32).mul_(0.01).to(torch.bfloat16))
+    P = torch.from_numpy(rig.projection_matrices(Rv.astype(np.float64))).to(dev)
+    return chain, rig, Rv, q, maps, P
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mvgeo
+    from mvgeo import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = mvgeo._lib.load()
+
+    chain, rig, Rv, q, maps, P = make_inputs(mvgeo, torch, dev, rank)
+    K = chain.n_points
+    cams = ops.cameras_to_device(rig, dev)
+    Rvt = torch.from_numpy(Rv).to(dev)
+    out = mvgeo.alloc_outputs(B, V, K, dev)
+    Hi, Wi = rig.image_size
+    sx, sy = Wi / W, Hi / H
+    n_maps = B * V * K
+    st = torch.cuda.current_stream(dev)
+    import ctypes as C
+
+    def step():
+        """decode -> triangulate -> FK + reprojection consistency through the C ABI (the same three
+        launches mvgeo_pipeline makes), with CUDA events around the decode kernel."""
+        s = st.cuda_stream
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        rc = lib.mvgeo_decode(maps.data_ptr(), mvgeo._lib.BF16, n_maps, H, W, sx, sy, mvgeo._lib.SOFT_GLOBAL, BETA, 0, 0,
+                              1, 1, 0, out["idx"].data_ptr(), out["peak"].data_ptr(), out["score"].data_ptr(),
+                              out["kp_hard"].data_ptr(), out["kp_soft"].data_ptr(), s)
+        e1.record(st)
+        rc |= lib.mvgeo_triangulate(out["kp_soft"].data_ptr(), out["score"].data_ptr(), P.data_ptr(), B, V, K, MIN_SCORE, 0,
+                                    out["X_tri"].data_ptr(), out["tri_resid"].data_ptr(), out["tri_views"].data_ptr(), s)
+        rc |= lib.mvgeo_fk_reproj_fwd(C.byref(chain.struct), q.data_ptr(), B, Rvt.data_ptr(), cams.data_ptr(), V,
+                                      out["kp_soft"].data_ptr(), None, 1.0, out["X_fk"].data_ptr(), out["uv_fk"].data_ptr(),
+                                      out["frame_loss"].data_ptr(), out["loss"].data_ptr(), s)
+        assert rc == 0, rc
+        if world > 1:  # the path's only communication: final result gather, < 1 KB per frame
+            mvgeo.sharding.gather_frames({k: out[k] for k in ("X_tri", "kp_soft", "score")}, B * world)
+        return e0, e1
+
+    def fence():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(st)
+    dec_events = [step() for _ in range(args.steps)]
+    t_end.record(st)
+    fence()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    dec_ms = [a.elapsed_time(b) for a, b in dec_events]
+    loss = float(out["loss"])
+    assert np.isfinite(loss)
+
+    # ---------------- e2e: host buffers through the C-ABI context (H2D + kernels + D2H timed)
+    e2e_steps = max(1, min(args.steps, 5))
+    hp = mvgeo.HostPipeline(chain, rig, Rv, dtype=torch.bfloat16, H=H, W=W, image_size=rig.image_size, soft="global",
+                            beta=BETA, min_score=MIN_SCORE, chunk_frames=64, device=local)
+    maps_h = torch.empty(maps.shape, dtype=maps.dtype).pin_memory()
+    maps_h.copy_(maps)
+    q_h = q.cpu().pin_memory()
+    out_h = mvgeo.alloc_outputs(B, V, K, None, pin=True)
+    hp.run(maps_h, q_h, out_h)  # warm-up
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hp.run(maps_h, q_h, out_h)  # synchronous on return: results are in host memory
+    e2e_s = time.perf_counter() - t0
+    assert np.isfinite(float(out_h["loss"]))
+    assert torch.equal(out_h["idx"], out["idx"].cpu()), "host pipeline and device pipeline disagree"
+    hp.close()
+    h2d = maps_h.numel() * maps_h.element_size() + q_h.numel() * 4 + V * (12 + 9 + 24) * 4
+    d2h = sum(t.numel() * t.element_size() for n, t in out_h.items() if isinstance(t, torch.Tensor) and n != "loss")
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s, statistics.mean(dec_ms)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_s, dec_mean = (float(x) for x in t)
+    else:
+        dec_mean = statistics.mean(dec_ms)
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        frame_bytes = V * K * H * W * 2
+        achieved = frame_bytes * B / (dec_mean * 1e-3) / 1e9
+        value = B * world * args.steps / (elapsed_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "robot": ROBOT, "views": V, "keypoints": K, "frames_per_gpu_per_step": B,
+                       "map": [H, W], "map_dtype": "bf16", "soft_argmax": f"global beta={BETA}",
+                       "l2": "inputs are 5.03 GB per step per GPU (>> 126 MB L2): no flush needed",
+                       "result_gather": "nccl all_gather per step" if world > 1 else "none (1 GPU)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "decode_vec_kernel<bf16, global>", "peak_source": peak_src,
+                         "decode_ms": dec_mean, "decode_share_of_step": dec_mean * args.steps / elapsed_ms,
+                         "frac_of_nominal_8TBps": achieved / 8000.0, "bytes_per_frame": frame_bytes},
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "mvgeo_pipeline_host (pinned host buffers)"},
+            "gpu_launches": 4 * args.steps,
+            "clocks": clocks,
+            "check": {"loss": loss},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import cpu_pipeline as cp
+
+            fps, workers, total, desc = cp.timed_throughput(ROBOT, V, H, W, (1200, 1920), _intrinsics(), frames_per_worker=4,
+                                                            min_seconds=10.0)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port", "sample": desc}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

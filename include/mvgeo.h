@@ -252,7 +252,7 @@ int mvgeo_pipeline(const mvgeo_pipeline_cfg* cfg, const void* maps, int64_t B,
  * overlaps H2D of frame chunk i+1 with the kernels of chunk i. Synchronous on return. */
 typedef struct mvgeo_ctx mvgeo_ctx;
 int mvgeo_ctx_create(mvgeo_ctx** ctx, int device, const mvgeo_pipeline_cfg* cfg,
-                     const mvgeo_chain* chain, int n_joints_in, int64_t chunk_frames);
+                     const mvgeo_chain* chain, int64_t chunk_frames);
 int mvgeo_ctx_destroy(mvgeo_ctx* ctx);
 int mvgeo_pipeline_host(mvgeo_ctx* ctx, const void* maps_host, int64_t B,
                         const float* P_host, const float* q_host, const float* R_view_host,

@@ -1,0 +1,511 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI, via mvgeo.ops / mvgeo.compat)
+against the oracle on identical seeded inputs and against the reference golden vectors.
+
+Tolerances (BASELINE.json north_star): arg-max indices bit-exact; sub-pixel key-points
+<= 1e-3 px; triangulated points and FK joint positions <= 1e-5 (relative, metres);
+gradients 1e-4 relative against float64 autograd."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvgeo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+_mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mg)
+INP = _mg.gen_inputs()
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def mv():
+    import mvgeo
+
+    assert os.path.isfile(mvgeo.LIB_PATH), "libmvgeo.so must be built in-tree (make)"
+    mvgeo._lib.load()
+    return mvgeo
+
+
+def _to_np32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _as_dtype(a, dtype):
+    """numpy float32 -> torch tensor of dtype on the GPU, plus the exactly-representable float32 view
+    of what the GPU sees (bf16/fp16 rounding applied) for the oracle."""
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV).to(dtype)
+    return t, t.float().cpu().numpy()
+
+
+# =========================================================================== decode
+@pytest.mark.parametrize("shape", [(3, 7, 24, 40), (2, 3, 31, 33), (2, 8, 120, 160), (1, 7, 128, 128), (5, 5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_decode_argmax_bit_exact(mv, shape, dtype):
+    rng = np.random.default_rng(1000 + sum(shape) + {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype])
+    a = rng.normal(0, 1, size=shape).astype(np.float32)
+    t, a_seen = _as_dtype(a, dtype)
+    r = mv.decode_heatmaps(t, (1200, 1920), soft=None, apply_sigmoid=True)
+    H, W = shape[-2:]
+    d = O.decode(a_seen, 1920 / W, 1200 / H, apply_sigmoid=True)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), d["idx"])  # bit-exact, incl. bf16/fp16 ties
+    np.testing.assert_array_equal(_to_np32(r.peak), d["peak"])
+    np.testing.assert_array_equal(_to_np32(r.kp_hard), d["kp_hard"])  # double product rounded once
+    np.testing.assert_allclose(_to_np32(r.score), d["score"], rtol=2e-6)
+    np.testing.assert_array_equal(_to_np32(r.kp_soft), d["kp_hard"])  # soft=None -> hard key-points
+
+
+def test_decode_golden_reference_vectors(mv):
+    for f in range(5):
+        r = mv.decode_heatmaps(torch.from_numpy(INP["maps_small"][f]).to(DEV), (1200, 1920), soft=None, apply_sigmoid=True)
+        np.testing.assert_array_equal(r.idx.cpu().numpy(), G["dec_small_rawidx"][f])
+        np.testing.assert_array_equal(_to_np32(r.kp_hard), G["dec_small_kp"][f])
+        np.testing.assert_allclose(_to_np32(r.score), G["dec_small_score"][f], rtol=2e-6)
+    # native 7x128x128: the reference argmaxes sigmoid(h); indices may differ only inside a sigmoid tie
+    t = torch.from_numpy(INP["maps_native"])
+    r = mv.decode_heatmaps(t.to(DEV), (1080, 1920), soft=None, apply_sigmoid=True)
+    np.testing.assert_allclose(_to_np32(r.score), G["dec_native_score"], rtol=2e-6)
+    sig = t.sigmoid().reshape(7, -1)
+    ours = r.idx.cpu().long()
+    ref_idx = sig.argmax(dim=1)
+    assert torch.equal(sig[torch.arange(7), ours], sig[torch.arange(7), ref_idx])  # same tie class
+    # inline arg-max call sites (DIP_REAL.py:120): coarse maps with many exact ties
+    r = mv.decode_heatmaps(torch.from_numpy(INP["maps_ties"]).to(DEV), None, soft=None)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), G["dec_ties_idx"])
+
+
+def test_decode_edge_cases(mv):
+    H, W = 16, 24
+    a = np.zeros((6, H, W), dtype=np.float32)
+    a[0, 3, 5] = a[0, 9, 1] = 2.0                      # tie: first wins
+    a[1] = -np.inf                                     # all -inf -> index 0
+    a[2, 4, 4], a[2, 7, 7], a[2, 2, 20] = 5.0, np.nan, np.nan   # NaN maximal, first NaN
+    a[3] = -0.0
+    a[3, 10, 3] = 0.0                                  # -0 == +0 -> index 0
+    a[4] = -3.0
+    a[4, H - 1, W - 1] = -1.0                          # last element
+    a[5, 0, 0] = 1.0                                   # first element
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
+        t, seen = _as_dtype(a, dtype)
+        for soft in (None, "global", "window"):
+            r = mv.decode_heatmaps(t, None, soft=soft, beta=20.0)
+            idx = r.idx.cpu().numpy()
+            np.testing.assert_array_equal(idx, [3 * W + 5, 0, 2 * W + 20, 0, H * W - 1, 0])
+            np.testing.assert_array_equal(idx, O.argmax_first(seen)[0])
+            np.testing.assert_array_equal(idx, [int(torch.argmax(t[i].float().cpu())) for i in range(6)])
+            ks = _to_np32(r.kp_soft)
+            if soft is not None:
+                assert np.all(np.isnan(ks[2]))                       # NaN peak -> NaN
+                np.testing.assert_array_equal(ks[1], [0, 0])         # all -inf -> hard peak
+    # empty input
+    r = mv.decode_heatmaps(torch.empty((0, 7, 8, 8), device=DEV), None)
+    assert r.idx.shape == (0, 7)
+    with pytest.raises(ValueError):
+        mv.decode_heatmaps(torch.zeros((2, 8, 8)), None)              # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        mv.decode_heatmaps(torch.zeros((2, 8, 8), device=DEV), None, soft="global", beta=0.0)
+    with pytest.raises(ValueError):
+        mv.decode_heatmaps(torch.zeros((2, 8, 8), device=DEV), None, soft="window", window_radius=99)
+
+
+def _blob_maps(rng, n, H, W, sigma=3.0, noise=0.01):
+    yy, xx = np.mgrid[0:H, 0:W]
+    c = np.stack([rng.uniform(-2, W + 2, n), rng.uniform(-2, H + 2, n)], axis=1)
+    m = np.exp(-((xx[None] - c[:, 0, None, None]) ** 2 + (yy[None] - c[:, 1, None, None]) ** 2) / (2 * sigma ** 2))
+    return (m + rng.normal(0, noise, m.shape)).astype(np.float32), c
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("HW", [(48, 64), (120, 160), (37, 41)])
+def test_decode_soft_argmax_within_1e3_px(mv, dtype, HW):
+    rng = np.random.default_rng(17)
+    H, W = HW
+    a, _ = _blob_maps(rng, 24, H, W)
+    a[-2] = rng.uniform(0, 1, (H, W))        # flat map: nothing can be skipped
+    a[-1] = 0.25                             # constant map: centroid of the whole map
+    t, seen = _as_dtype(a, dtype)
+    sx, sy = 1920 / W, 1200 / H
+    for beta in (8.0, 60.0, 400.0):
+        r = mv.decode_heatmaps(t, (1200, 1920), soft="global", beta=beta)
+        ref = O.soft_argmax(seen, beta, "global") * [sx, sy]
+        err = np.abs(_to_np32(r.kp_soft) - ref) / [sx, sy]           # in MAP pixels
+        assert err.max() < 1e-3, (beta, err.max())
+        for radius in (0, 2, 5, 15):
+            r = mv.decode_heatmaps(t, (1200, 1920), soft="window", beta=beta, window_radius=radius)
+            ref = O.soft_argmax(seen, beta, "window", radius) * [sx, sy]
+            err = np.abs(_to_np32(r.kp_soft) - ref) / [sx, sy]
+            assert err.max() < 1e-3, (beta, radius, err.max())
+
+
+@pytest.mark.parametrize("dtype,HW", [(torch.bfloat16, (480, 640)), (torch.float32, (480, 640)), (torch.bfloat16, (240, 320)),
+                                      (torch.float32, (600, 1000))])
+def test_decode_cluster_split_maps(mv, dtype, HW):
+    """Maps above 192 KB are split across a thread-block cluster (DSMEM combine)."""
+    rng = np.random.default_rng(23)
+    H, W = HW
+    a, _ = _blob_maps(rng, 5, H, W, sigma=4.0)
+    a[3] = np.round(a[3] * 8) / 8            # heavy ties across cluster ranks
+    a[4, H - 1, W - 3] = 9.0                 # peak in the last segment
+    t, seen = _as_dtype(a, dtype)
+    r = mv.decode_heatmaps(t, None, soft="global", beta=50.0)
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), O.argmax_first(seen)[0])
+    ref = O.soft_argmax(seen, 50.0, "global")
+    assert np.abs(_to_np32(r.kp_soft) - ref).max() < 1e-3
+    r = mv.decode_heatmaps(t, None, soft="window", beta=50.0, window_radius=4)
+    assert np.abs(_to_np32(r.kp_soft) - O.soft_argmax(seen, 50.0, "window", 4)).max() < 1e-3
+
+
+def test_decode_view_list_equals_stacked(mv):
+    rng = np.random.default_rng(5)
+    views = [torch.from_numpy(rng.normal(size=(6, 7, 32, 32)).astype(np.float32)).to(DEV) for _ in range(3)]
+    a = mv.decode_heatmaps(views, (1200, 1920), soft="global", beta=30.0)
+    b = mv.decode_heatmaps(torch.stack(views, dim=1), (1200, 1920), soft="global", beta=30.0)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)
+
+
+def test_decode_unaligned_base_pointer(mv):
+    rng = np.random.default_rng(9)
+    buf = torch.from_numpy(rng.normal(size=(4 * 32 * 32 + 1,)).astype(np.float32)).to(DEV)
+    t = buf[1:].view(4, 32, 32)  # 4-byte aligned only -> generic kernel
+    assert t.data_ptr() % 16 != 0
+    r = mv.decode_heatmaps(t, None, soft="global", beta=10.0)
+    seen = t.cpu().numpy()
+    np.testing.assert_array_equal(r.idx.cpu().numpy(), O.argmax_first(seen)[0])
+    assert np.abs(_to_np32(r.kp_soft) - O.soft_argmax(seen, 10.0, "global")).max() < 1e-3
+
+
+# =============================================================================== FK
+def _chain_and_q(mv, robot):
+    if robot == "fr3":
+        return mv.Chain.builtin("fr3"), INP["fr3_q"], [("view1", "fr3_fk_view1"), ("none", "fr3_fk_noview")]
+    if robot == "fr5":
+        q = np.concatenate([INP["fr5_q_rand"], G["fr5_q_real"]], axis=0)
+        return mv.Chain.builtin("fr5"), q, [(v, f"fr5_fk_{v}") for v in ("top", "left", "right", "none")]
+    return mv.Chain.builtin("meca500"), INP["meca_q"], [("none", "meca_fk")]
+
+
+@pytest.mark.parametrize("robot", ["fr3", "fr5", "meca500"])
+def test_fk_golden_1e5(mv, robot):
+    chain, q, cases = _chain_and_q(mv, robot)
+    Rv = np.stack([np.asarray(mv.view_rotation(robot, v), dtype=np.float32) for v, _ in cases])
+    X = _to_np32(mv.forward_kinematics(chain, torch.from_numpy(q.astype(np.float32)).to(DEV), Rv))
+    assert X.shape == (q.shape[0], len(cases), chain.n_points, 3)
+    for vi, (_, key) in enumerate(cases):
+        # float32 inputs vs the reference's float64 inputs: 1e-5 relative to the arm's reach
+        np.testing.assert_allclose(X[:, vi], G[key], rtol=1e-5, atol=1e-5)
+    # identical float32 inputs through the float64 oracle: tighter
+    Xo = O.fk_chain(O.chain_spec(robot), q.astype(np.float32), Rv)
+    np.testing.assert_allclose(X, Xo, rtol=0, atol=3e-6)
+
+
+def test_fk_generic_chain(mv):
+    dh = INP["generic_dh"]
+    chain = mv.Chain.from_dh(list(dh[:, 2]), list(dh[:, 1]), list(dh[:, 3]), list(dh[:, 0]), "standard", 1.0, emit_base=False)
+    X = _to_np32(mv.forward_kinematics(chain, torch.from_numpy(INP["generic_angles"]).to(DEV)))[:, 0]
+    np.testing.assert_allclose(X, G["generic_fk"], rtol=1e-5, atol=2e-6)
+    fk = mv.compat.ForwardKinematics([tuple(r) for r in dh])
+    out = fk.forward(torch.from_numpy(INP["generic_angles"]))
+    assert out.dtype == torch.float32 and not out.is_cuda
+    np.testing.assert_allclose(out.numpy(), G["generic_fk"], rtol=1e-5, atol=2e-6)
+    with pytest.raises(ValueError):
+        mv.forward_kinematics(chain, torch.zeros((2, 3), device=DEV))
+
+
+def test_compat_shims_match_reference(mv):
+    c = mv.compat
+    for i in (0, 1, 5):
+        p = c.fr3.angle_to_joint_coordinate(list(INP["fr3_q"][i]), "view1")
+        assert p.dtype == np.float32 and p.shape == (8, 3)
+        np.testing.assert_allclose(p, G["fr3_fk_view1"][i], rtol=1e-5, atol=1e-5)
+        ar = dict(rvec_x=INP["proj_rvec"][i, 0], rvec_y=INP["proj_rvec"][i, 1], rvec_z=INP["proj_rvec"][i, 2],
+                  tvec_x=INP["proj_tvec"][i, 0], tvec_y=INP["proj_tvec"][i, 1], tvec_z=INP["proj_tvec"][i, 2])
+        K0, d0 = G["zedx_K"][0].astype(np.float32), G["zedx_dist"][0].astype(np.float32)
+        uv = c.fr3.joint_coordinate_to_pixel_plane(G["fr3_fk_view1"][i], ar, K0, np.zeros(5, np.float32))
+        np.testing.assert_allclose(uv, G["proj_fr3_zero"][i], rtol=1e-5, atol=2e-3)
+        uv = c.fr3.joint_coordinate_to_pixel_plane(G["fr3_fk_view1"][i], ar, K0, d0)
+        np.testing.assert_allclose(uv, G["proj_fr3_real"][i], rtol=1e-5, atol=2e-3)
+        ar_deg = {k: (float(np.degrees(v)) if k.startswith("rvec") else v) for k, v in ar.items()}
+        uv = c.fr5.joint_coordinate_to_pixel_plane(G["fr5_fk_top"][i], ar_deg, K0, d0)
+        np.testing.assert_allclose(uv, G["proj_fr5_real_degrvec"][i], rtol=1e-5, atol=2e-3)
+    q5 = np.concatenate([INP["fr5_q_rand"], G["fr5_q_real"]], axis=0)
+    np.testing.assert_allclose(c.fr5.angle_to_joint_coordinate(q5[30], "left"), G["fr5_fk_left"][30], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(c.meca500.forward_kinematics(INP["meca_q"][1]), G["meca_fk"][1], rtol=1e-5, atol=1e-5)
+    uv = c.meca500.project_to_pixel(G["meca_fk"][1], np.deg2rad(np.array([96, 98, -45], np.float32)),
+                                    np.array([0, -0.01, 0.75], np.float32), G["zedx_K"][0].astype(np.float32),
+                                    G["zedx_dist"][0].astype(np.float32))
+    np.testing.assert_allclose(uv, G["proj_meca_prior"], rtol=1e-5, atol=2e-3)
+    uv = c.project_3d_to_2d(torch.from_numpy(G["generic_fk"]), G["zedx_K"][0], None,
+                            rvec=[INP["proj_rvec"][i].reshape(3, 1) for i in range(6)],
+                            tvec=[INP["proj_tvec"][i].reshape(3, 1) for i in range(6)])
+    np.testing.assert_allclose(uv.numpy(), G["proj_generic"], rtol=1e-5, atol=2e-3)
+    kp, sc = c.extract_keypoints_from_heatmaps(torch.from_numpy(INP["maps_small"][2]), (1200, 1920))
+    np.testing.assert_array_equal(kp, G["dec_small_kp"][2])
+    np.testing.assert_allclose(sc, G["dec_small_score"][2], rtol=2e-6)
+    assert kp.dtype == np.float32 and sc.dtype == np.float32
+    kps = c.decode_argmax(torch.from_numpy(INP["maps_ties"][1]), (1200, 1920))
+    np.testing.assert_array_equal(kps, O.decode_inline_argmax(torch.from_numpy(INP["maps_ties"][1]), (1200, 1920)))
+    m = c.create_gt_heatmap((40.3, 77.8), (128, 128), 5.0)
+    assert m.dtype == np.float64
+    np.testing.assert_allclose(m, G["gt_maps_128"][0], rtol=0, atol=2e-6)
+
+
+# ======================================================================== projection
+def test_projection_vs_oracle_with_distortion(mv):
+    rng = np.random.default_rng(31)
+    rig = mv.CameraRig.synthetic_ring(5, distortion=True)
+    X = (rng.uniform(-0.6, 0.6, size=(40, 9, 3)) + [0, 0, 0.4]).astype(np.float32)
+    uv = _to_np32(mv.project_points(torch.from_numpy(X).to(DEV), rig))
+    for v in range(5):
+        ref = O.project_points(X, rig.R[v].astype(np.float32), rig.t[v].astype(np.float32), rig.K[v].astype(np.float32),
+                               rig.dist[v].astype(np.float32))
+        np.testing.assert_allclose(uv[:, v], ref, rtol=1e-5, atol=2e-3)
+    Xv = np.repeat(X[:, None], 5, axis=1).copy()
+    uv2 = _to_np32(mv.project_points(torch.from_numpy(Xv).to(DEV), rig))
+    np.testing.assert_array_equal(uv, uv2)
+
+
+# ===================================================================== triangulation
+@pytest.mark.parametrize("V", [2, 3, 4, 8])
+def test_triangulate_vs_float64_svd(mv, V):
+    rng = np.random.default_rng(100 + V)
+    rig = mv.CameraRig.synthetic_ring(V)
+    P = rig.projection_matrices()
+    B, K = 64, 8
+    X = rng.uniform(-0.6, 0.6, size=(B, K, 3)) + [0, 0, 0.4]
+    X[:, 0] = 0.0  # robot base at the world origin
+    kp = np.stack([O.project_points(X, rig.R[v], rig.t[v], rig.K[v]) for v in range(V)], axis=1)
+    for noise in (0.0, 0.5, 3.0):
+        kpn = (kp + noise * rng.normal(size=kp.shape)).astype(np.float32)
+        Xo, ro, no = O.triangulate_dlt(kpn, P)
+        Xg, rg, ng = mv.triangulate(torch.from_numpy(kpn).to(DEV), torch.from_numpy(P).to(DEV))
+        err = np.linalg.norm(_to_np32(Xg) - Xo, axis=-1) / np.maximum(np.linalg.norm(Xo, axis=-1), 1.0)
+        assert err.max() < 1e-5, (noise, err.max())
+        np.testing.assert_array_equal(ng.cpu().numpy(), no)
+        np.testing.assert_allclose(_to_np32(rg), ro, rtol=2e-3, atol=2e-3)
+        if noise == 0.0:
+            assert np.abs(_to_np32(Xg) - X).max() < 2e-5  # closed loop: recovers the true points
+
+
+def test_triangulate_weights_and_invalid_views(mv):
+    rng = np.random.default_rng(41)
+    V, B, K = 4, 16, 7
+    rig = mv.CameraRig.synthetic_ring(V)
+    P = rig.projection_matrices()
+    X = rng.uniform(-0.5, 0.5, size=(B, K, 3)) + [0, 0, 0.4]
+    kp = np.stack([O.project_points(X, rig.R[v], rig.t[v], rig.K[v]) for v in range(V)], axis=1)
+    kp = (kp + rng.normal(0, 1.0, kp.shape)).astype(np.float32)
+    w = rng.uniform(0.2, 1.0, size=(B, V, K)).astype(np.float32)
+    w[0, 1:, 2] = 0.05        # one valid view -> NaN
+    w[1, 2:, 3] = 0.05        # exactly two valid views
+    kp[2, 0, 4] = np.nan      # non-finite key-point drops the view
+    w[3, :, 5] = 0.0          # no valid view
+    for weighted in (False, True):
+        Xo, ro, no = O.triangulate_dlt(kp, P, w, min_weight=0.1, weighted=weighted)
+        Xg, rg, ng = mv.triangulate(torch.from_numpy(kp).to(DEV), torch.from_numpy(P).to(DEV), torch.from_numpy(w).to(DEV),
+                                    min_weight=0.1, weighted=weighted)
+        Xg, ng = _to_np32(Xg), ng.cpu().numpy()
+        np.testing.assert_array_equal(ng, no)
+        assert ng[0, 2] == 1 and ng[1, 3] == 2 and ng[2, 4] == 3 and ng[3, 5] == 0
+        np.testing.assert_array_equal(np.isnan(Xg), np.isnan(Xo))
+        ok = ~np.isnan(Xo)
+        err = np.abs(Xg[ok] - Xo[ok])
+        assert err.max() < 1e-5 * max(1.0, np.abs(Xo[ok]).max())
+        assert np.all(np.isnan(_to_np32(rg)[np.isnan(Xo).any(-1)]))
+    X0 = mv.triangulate(torch.empty((0, V, K, 2), device=DEV), torch.from_numpy(P).to(DEV))[0]
+    assert X0.shape == (0, K, 3)
+
+
+# ============================================================ FK + reprojection loss
+@pytest.mark.parametrize("robot,lo,hi", [("fr3", -2.5, 2.5), ("fr5", -170.0, 170.0), ("meca500", -150.0, 150.0)])
+@pytest.mark.parametrize("distortion", [False, True])
+def test_fk_reproj_loss_forward_backward(mv, robot, lo, hi, distortion):
+    rng = np.random.default_rng(77)
+    chain = mv.Chain.builtin(robot)
+    V, B, J, K = 3, 33, chain.n_joints, chain.n_points
+    rig = mv.CameraRig.synthetic_ring(V, distortion=distortion)
+    views = (list(mv.VIEW_EULER_ZYX_DEG[robot]) + [None] * V)[:V]
+    Rv = np.stack([np.asarray(mv.view_rotation(robot, v)) for v in views]).astype(np.float32)
+    q = rng.uniform(lo, hi, size=(B, J)).astype(np.float32)
+    spec = O.chain_spec(robot)
+    cams = [dict(R=rig.R[v].astype(np.float32), t=rig.t[v].astype(np.float32), K=rig.K[v].astype(np.float32),
+                 dist=rig.dist[v].astype(np.float32)) for v in range(V)]
+    qt = torch.tensor(q.astype(np.float64), requires_grad=True)
+    with torch.no_grad():
+        _, _, uv0 = O.fk_reproj_loss_torch(spec, qt, Rv, cams, np.zeros((B, V, K, 2)))
+    gt = (uv0.numpy() + rng.normal(0, 4.0, uv0.shape)).astype(np.float32)
+    gt[1, 0, 2] = np.nan  # skipped point
+    w = rng.uniform(0.0, 1.0, size=(B, V, K)).astype(np.float32)
+    for wt in (None, w):
+        lo_, Xo, uvo = O.fk_reproj_loss_torch(spec, qt, Rv, cams, gt, wt, 0.7)
+        (go,) = torch.autograd.grad(lo_, qt)
+        qg = torch.from_numpy(q).to(DEV).requires_grad_(True)
+        loss, X, uv, fl = mv.fk_reproj_loss(chain, qg, rig, torch.from_numpy(gt).to(DEV), Rv,
+                                            None if wt is None else torch.from_numpy(wt).to(DEV), lam=0.7)
+        np.testing.assert_allclose(_to_np32(X), Xo.detach().numpy(), rtol=0, atol=3e-6)
+        np.testing.assert_allclose(_to_np32(uv), uvo.detach().numpy(), rtol=1e-5, atol=2e-3)
+        assert abs(float(loss) - float(lo_)) <= 1e-4 * abs(float(lo_))
+        assert abs(float(fl.sum()) - float(loss)) <= 1e-5 * abs(float(loss))
+        (loss * 3.0).backward()
+        g = _to_np32(qg.grad) / 3.0
+        scale = np.abs(go.numpy()).max()
+        assert np.abs(g - go.numpy()).max() <= 1e-4 * scale, np.abs(g - go.numpy()).max() / scale
+
+
+# ========================================================== GT encoder and heat-map MSE
+def test_encode_gaussian_vs_reference(mv):
+    kp = torch.from_numpy(INP["gt_kp"].astype(np.float32)).to(DEV)
+    m = _to_np32(mv.encode_gaussian(kp, (128, 128), 5.0))
+    np.testing.assert_allclose(m, G["gt_maps_128"], rtol=0, atol=2e-6)
+    assert int(np.argmax(m[0])) == 78 * 128 + 40
+    kp2 = torch.from_numpy((INP["gt_kp"] * [0.3, 0.2]).astype(np.float32)).to(DEV)
+    for dtype, tol in ((torch.float32, 2e-6), (torch.bfloat16, 4e-3), (torch.float16, 5e-4)):
+        m = _to_np32(mv.encode_gaussian(kp2, (24, 40), 3.0, dtype))
+        np.testing.assert_allclose(m, G["gt_maps_rect"], rtol=0, atol=tol)
+    m = _to_np32(mv.encode_gaussian(torch.tensor([[np.nan, 3.0]], device=DEV), (9, 11), 2.0))  # odd size: scalar path
+    assert m.shape == (1, 9, 11) and np.all(m == 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("HW", [(24, 40), (9, 11)])
+def test_heatmap_mse_forward_backward(mv, dtype, HW):
+    rng = np.random.default_rng(3)
+    H, W = HW
+    pred = rng.normal(0, 0.3, size=(2, 3, H, W)).astype(np.float32)
+    kp = np.stack([rng.uniform(0, W, (2, 3)), rng.uniform(0, H, (2, 3))], axis=-1).astype(np.float32)
+    kp[1, 1] = np.nan
+    t, seen = _as_dtype(pred, dtype)
+    t.requires_grad_(True)
+    loss = mv.heatmap_mse_loss(t, torch.from_numpy(kp).to(DEV), 3.0, 100.0)
+    lo, go = O.heatmap_mse(seen.reshape(-1, H, W), kp.reshape(-1, 2), 3.0, 100.0)
+    assert abs(float(loss) - lo) <= 2e-5 * abs(lo)
+    (loss * 0.5).backward()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    np.testing.assert_allclose(_to_np32(t.grad).reshape(-1, H, W) * 2.0, go, rtol=tol, atol=tol * np.abs(go).max())
+
+
+# ================================================================= fused pipeline
+def _closed_loop_inputs(mv, robot, V, B, H, W, dtype, seed=0):
+    """FK -> project -> Gaussian belief maps (all on the GPU, through the kernels under test)."""
+    rng = np.random.default_rng(seed)
+    chain = mv.Chain.builtin(robot)
+    rig = mv.CameraRig.synthetic_ring(V)
+    views = (list(mv.VIEW_EULER_ZYX_DEG[robot]) + [None] * V)[:V]
+    Rv = np.stack([np.asarray(mv.view_rotation(robot, v)) for v in views]).astype(np.float32)
+    lim = 2.0 if robot == "fr3" else 120.0
+    q = torch.from_numpy(rng.uniform(-lim, lim, size=(B, chain.n_joints)).astype(np.float32)).to(DEV)
+    X = mv.forward_kinematics(chain, q, Rv)
+    uv = mv.project_points(X, rig)                                  # image pixels
+    Hi, Wi = rig.image_size
+    kp_map = uv * torch.tensor([W / Wi, H / Hi], device=DEV)
+    maps = mv.encode_gaussian(kp_map, (H, W), 3.0, dtype)
+    P = torch.from_numpy(rig.projection_matrices(Rv.astype(np.float64))).to(DEV)
+    return chain, rig, Rv, q, X, uv, maps, P
+
+
+@pytest.mark.parametrize("robot,V,dtype", [("fr3", 3, torch.float32), ("fr3", 4, torch.bfloat16), ("meca500", 4, torch.bfloat16),
+                                           ("fr5", 3, torch.float16)])
+def test_pipeline_matches_oracle_and_closes_the_loop(mv, robot, V, dtype):
+    B, H, W = 12, 120, 160
+    chain, rig, Rv, q, X, uv, maps, P = _closed_loop_inputs(mv, robot, V, B, H, W, dtype)
+    out = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global", beta=100.0, min_score=0.3)
+    K = chain.n_points
+    seen = maps.float().cpu().numpy()
+    Hi, Wi = rig.image_size
+    d = O.decode(seen, Wi / W, Hi / H, "global", 100.0)
+    np.testing.assert_array_equal(out["idx"].cpu().numpy(), d["idx"])
+    np.testing.assert_array_equal(_to_np32(out["kp_hard"]), d["kp_hard"])
+    assert (np.abs(_to_np32(out["kp_soft"]) - d["kp_soft"]) / [Wi / W, Hi / H]).max() < 1e-3
+    # triangulation of the GPU's own key-points vs the float64 SVD on the same key-points
+    kps = _to_np32(out["kp_soft"])
+    Xo, ro, no = O.triangulate_dlt(kps, P.cpu().numpy(), _to_np32(out["score"]), min_weight=0.3)
+    Xg = _to_np32(out["X_tri"])
+    np.testing.assert_array_equal(out["tri_views"].cpu().numpy(), no)
+    ok = ~np.isnan(Xo).any(-1)
+    assert ok.mean() > 0.7
+    err = np.linalg.norm(Xg[ok] - Xo[ok], axis=-1) / np.maximum(np.linalg.norm(Xo[ok], axis=-1), 1.0)
+    assert err.max() < 1e-5
+    # closed loop: triangulated points (base frame) equal FK in the base frame to sub-pixel accuracy
+    Xbase = _to_np32(mv.forward_kinematics(chain, q))[:, 0]
+    inside = (out["tri_views"].cpu().numpy() == V) & ok
+    assert np.abs(Xg[inside] - Xbase[inside]).max() < 5e-3  # 0.1 px at 160x120 ~ 1.2 px in the image ~ 2.5 mm
+    # FK leg equals the stand-alone kernels, consistency loss equals its definition
+    assert torch.allclose(out["X_fk"], X, rtol=0, atol=1e-6) and torch.allclose(out["uv_fk"], uv, rtol=0, atol=1e-3)
+    diff = (uv - out["kp_soft"]).double()
+    ref_loss = float((diff ** 2).sum() / (B * V * K * 2))
+    assert abs(float(out["loss"]) - ref_loss) <= 1e-4 * ref_loss + 1e-12
+
+
+def test_pipeline_shard_invariance_and_graph_capture(mv):
+    chain, rig, Rv, q, X, uv, maps, P = _closed_loop_inputs(mv, "fr3", 4, 10, 64, 96, torch.bfloat16, seed=3)
+    full = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global")
+    for a, b in ((0, 3), (3, 10), (9, 10)):
+        part = mv.pipeline(maps[a:b].contiguous(), P, chain, q[a:b].contiguous(), rig, Rv, image_size=rig.image_size, soft="global")
+        for name in ("idx", "peak", "score", "kp_hard", "kp_soft", "X_tri", "tri_resid", "tri_views", "X_fk", "uv_fk"):
+            assert torch.equal(part[name], full[name][a:b]), name   # bit-identical however frames are sharded
+    # CUDA-graph capture of the three launches
+    cams = mv.ops.cameras_to_device(rig, DEV)
+    Rvt = torch.from_numpy(Rv).to(DEV)
+    out = mv.alloc_outputs(10, 4, chain.n_points, DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        mv.pipeline(maps, P, chain, q, cams, Rvt, image_size=rig.image_size, soft="global", out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    for t in out.values():
+        if isinstance(t, torch.Tensor):
+            t.zero_()
+    with torch.cuda.graph(g):
+        mv.pipeline(maps, P, chain, q, cams, Rvt, image_size=rig.image_size, soft="global", out=out)
+    g.replay()
+    torch.cuda.synchronize()
+    for name in ("idx", "kp_soft", "X_tri", "uv_fk", "loss"):
+        assert torch.equal(out[name], full[name]), name
+
+
+def test_host_pipeline_equals_device_pipeline(mv):
+    chain, rig, Rv, q, X, uv, maps, P = _closed_loop_inputs(mv, "meca500", 4, 21, 60, 80, torch.bfloat16, seed=8)
+    full = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="window", window_radius=4, min_score=0.2)
+    hp = mv.HostPipeline(chain, rig, Rv, dtype=torch.bfloat16, H=60, W=80, image_size=rig.image_size, soft="window",
+                         window_radius=4, min_score=0.2, chunk_frames=8)
+    out = hp.run(maps.cpu().pin_memory(), q.cpu().pin_memory())
+    for name in ("idx", "peak", "score", "kp_hard", "kp_soft", "X_tri", "tri_resid", "tri_views", "X_fk", "uv_fk"):
+        assert torch.equal(out[name], full[name].cpu()), name
+    assert abs(float(out["loss"]) - float(full["loss"])) <= 1e-5 * abs(float(full["loss"]))
+    hp.close()
+
+
+# =========================================== BASELINE.json full sizes: size-independent properties
+def test_full_size_round_trip_c2(mv):
+    """Config 2 shape (FR3, V=4, K=8, 240x320 bf16) at B=256 (1.26 GB): encode -> decode is the
+    identity on pixel centres, and the pipeline's triangulation returns FK (closed loop)."""
+    B, V, H, W = 256, 4, 240, 320
+    chain, rig, Rv, q, X, uv, maps, P = _closed_loop_inputs(mv, "fr3", V, B, H, W, torch.bfloat16, seed=12)
+    K = chain.n_points
+    out = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global", beta=100.0, min_score=0.5)
+    Hi, Wi = rig.image_size
+    kp_map = (uv * torch.tensor([W / Wi, H / Hi], device=DEV))
+    inb = (kp_map[..., 0] > 1) & (kp_map[..., 0] < W - 2) & (kp_map[..., 1] > 1) & (kp_map[..., 1] < H - 2)
+    idx = out["idx"].long()
+    px, py = (idx % W).float(), (idx // W).float()
+    # hard peak = nearest pixel centre of the encoded key-point (bf16 rounding can move it by one
+    # pixel when two neighbours round to the same value; first-maximum then picks the earlier one)
+    assert ((px - kp_map[..., 0]).abs()[inb] <= 1.0).all() and ((py - kp_map[..., 1]).abs()[inb] <= 1.0).all()
+    soft_map = out["kp_soft"] / torch.tensor([Wi / W, Hi / H], device=DEV)
+    assert (soft_map - kp_map).abs()[inb].max() < 0.2
+    allv = (out["tri_views"] == V) & inb.all(dim=1)
+    Xbase = mv.forward_kinematics(chain, q)[:, 0]
+    assert allv.float().mean() > 0.5
+    assert (out["X_tri"] - Xbase).abs()[allv].max() < 4e-3
+    # checksum of checksums: a second run is bit-identical (deterministic reductions)
+    out2 = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global", beta=100.0, min_score=0.5)
+    for name in ("idx", "kp_soft", "X_tri", "loss"):
+        assert torch.equal(out[name], out2[name])

@@ -219,24 +219,26 @@ def run_ours(args):
     assert np.isfinite(loss)
 
     # ---------------- e2e: host buffers through the C-ABI context (H2D + kernels + D2H timed)
-    e2e_steps = max(1, min(args.steps, 5))
-    hp = mvgeo.HostPipeline(chain, rig, Rv, dtype=torch.bfloat16, H=H, W=W, image_size=rig.image_size, soft="global",
-                            beta=BETA, min_score=MIN_SCORE, chunk_frames=64, device=local)
-    maps_h = torch.empty(maps.shape, dtype=maps.dtype).pin_memory()
-    maps_h.copy_(maps)
-    q_h = q.cpu().pin_memory()
-    out_h = mvgeo.alloc_outputs(B, V, K, None, pin=True)
-    hp.run(maps_h, q_h, out_h)  # warm-up
-    fence()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hp.run(maps_h, q_h, out_h)  # synchronous on return: results are in host memory
-    e2e_s = time.perf_counter() - t0
-    assert np.isfinite(float(out_h["loss"]))
-    assert torch.equal(out_h["idx"], out["idx"].cpu()), "host pipeline and device pipeline disagree"
-    hp.close()
-    h2d = maps_h.numel() * maps_h.element_size() + q_h.numel() * 4 + V * (12 + 9 + 24) * 4
-    d2h = sum(t.numel() * t.element_size() for n, t in out_h.items() if isinstance(t, torch.Tensor) and n != "loss")
+    e2e_steps, e2e_s, h2d, d2h = 0, float("nan"), 0, 0
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 5))
+        hp = mvgeo.HostPipeline(chain, rig, Rv, dtype=torch.bfloat16, H=H, W=W, image_size=rig.image_size, soft="global",
+                                beta=BETA, min_score=MIN_SCORE, chunk_frames=64, device=local)
+        maps_h = torch.empty(maps.shape, dtype=maps.dtype).pin_memory()
+        maps_h.copy_(maps)
+        q_h = q.cpu().pin_memory()
+        out_h = mvgeo.alloc_outputs(B, V, K, None, pin=True)
+        hp.run(maps_h, q_h, out_h)  # warm-up
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hp.run(maps_h, q_h, out_h)  # synchronous on return: results are in host memory
+        e2e_s = time.perf_counter() - t0
+        assert np.isfinite(float(out_h["loss"]))
+        assert torch.equal(out_h["idx"], out["idx"].cpu()), "host pipeline and device pipeline disagree"
+        hp.close()
+        h2d = maps_h.numel() * maps_h.element_size() + q_h.numel() * 4 + V * (12 + 9 + 24) * 4
+        d2h = sum(t.numel() * t.element_size() for n, t in out_h.items() if isinstance(t, torch.Tensor) and n != "loss")
 
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_s, statistics.mean(dec_ms)], device=dev, dtype=torch.float64)
@@ -262,7 +264,7 @@ def run_ours(args):
                          "traffic": None, "kernel": "decode_vec_kernel<bf16, global>", "peak_source": peak_src,
                          "decode_ms": dec_mean, "decode_share_of_step": dec_mean * args.steps / elapsed_ms,
                          "frac_of_nominal_8TBps": achieved / 8000.0, "bytes_per_frame": frame_bytes},
-            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": (B * world * e2e_steps / e2e_s) if e2e_steps else None, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "mvgeo_pipeline_host (pinned host buffers)"},
             "gpu_launches": 4 * args.steps,
             "clocks": clocks,
@@ -289,6 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -435,7 +435,17 @@ def test_pipeline_matches_oracle_and_closes_the_loop(mv, robot, V, dtype):
     # closed loop: triangulated points (base frame) equal FK in the base frame to sub-pixel accuracy
     Xbase = _to_np32(mv.forward_kinematics(chain, q))[:, 0]
     inside = (out["tri_views"].cpu().numpy() == V) & ok
-    assert np.abs(Xg[inside] - Xbase[inside]).max() < 5e-3  # 0.1 px at 160x120 ~ 1.2 px in the image ~ 2.5 mm
+    # beta=100 on a sigma-3 blob is nearly a hard peak: up to half a map pixel = 6 image px ~ 12 mm at 1.5 m
+    assert np.abs(Xg[inside] - Xbase[inside]).max() < 2.5e-2
+    # the windowed soft-arg-max (beta=15, r=5) is a genuine sub-pixel estimator: < 0.1 map px ~ 2.5 mm
+    outw = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="window", beta=15.0, window_radius=5,
+                       min_score=0.3)
+    Xw = _to_np32(outw["X_tri"])
+    insidew = (outw["tri_views"].cpu().numpy() == V) & ~np.isnan(Xw).any(-1)
+    kp_map = _to_np32(uv) * [W / Wi, H / Hi]
+    far = ((kp_map[..., 0] > 6) & (kp_map[..., 0] < W - 7) & (kp_map[..., 1] > 6) & (kp_map[..., 1] < H - 7)).all(axis=1)
+    assert (insidew & far).mean() > 0.3
+    assert np.abs(Xw[insidew & far] - Xbase[insidew & far]).max() < (4e-3 if dtype == torch.float32 else 8e-3)
     # FK leg equals the stand-alone kernels, consistency loss equals its definition
     assert torch.allclose(out["X_fk"], X, rtol=0, atol=1e-6) and torch.allclose(out["uv_fk"], uv, rtol=0, atol=1e-3)
     diff = (uv - out["kp_soft"]).double()
@@ -500,11 +510,11 @@ def test_full_size_round_trip_c2(mv):
     # pixel when two neighbours round to the same value; first-maximum then picks the earlier one)
     assert ((px - kp_map[..., 0]).abs()[inb] <= 1.0).all() and ((py - kp_map[..., 1]).abs()[inb] <= 1.0).all()
     soft_map = out["kp_soft"] / torch.tensor([Wi / W, Hi / H], device=DEV)
-    assert (soft_map - kp_map).abs()[inb].max() < 0.2
+    assert (soft_map - kp_map).abs()[inb].max() <= 0.51  # beta=100: nearly the hard peak, half-pixel bound
     allv = (out["tri_views"] == V) & inb.all(dim=1)
     Xbase = mv.forward_kinematics(chain, q)[:, 0]
     assert allv.float().mean() > 0.5
-    assert (out["X_tri"] - Xbase).abs()[allv].max() < 4e-3
+    assert (out["X_tri"] - Xbase).abs()[allv].max() < 1.2e-2
     # checksum of checksums: a second run is bit-identical (deterministic reductions)
     out2 = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global", beta=100.0, min_score=0.5)
     for name in ("idx", "kp_soft", "X_tri", "loss"):

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvgeo.so")
+# MVGEO_LIB overrides the path for kernel-development A/B builds only
+LIB_PATH = os.environ.get("MVGEO_LIB") or os.path.join(_HERE, "libmvgeo.so")
 
 MAX_JOINTS = 8
 MAX_VIEWS = 16

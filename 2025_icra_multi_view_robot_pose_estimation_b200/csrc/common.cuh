@@ -61,6 +61,41 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
+// ---- mbarrier + TMA bulk-copy primitives (async proxy; SASS: SYNCS.*, UBLKCP) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MVGEO_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MVGEO_DONE_%=;\n"
+      "bra MVGEO_WAIT_%=;\n"
+      "MVGEO_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0).
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // (value, index) ordering of torch.argmax: larger value wins, NaN is maximal, ties (equal
 // values, -0 == +0, or two NaNs) go to the lower index. True when (v2,i2) beats (v1,i1).
 __device__ __forceinline__ bool argmax_better(float v1, int i1, float v2, int i2) {
@@ -107,6 +142,11 @@ template <> struct Elem<MVGEO_F32> {
     const uint32_t w = j == 0 ? c.x : j == 1 ? c.y : j == 2 ? c.z : c.w;
     return __uint_as_float(w);
   }
+  // chunk maximum both as a float and in its shared-memory carrier form
+  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
+    cm = chunk_max(c);
+    packed = cm;
+  }
   __device__ static __forceinline__ carrier pack(float m) { return m; }
   __device__ static __forceinline__ float unpack(carrier m) { return m; }
   __device__ static __forceinline__ float load(const void* base, int64_t i) {
@@ -131,6 +171,13 @@ template <> struct Elem<MVGEO_BF16> {
   __device__ static __forceinline__ float get(const uint4& c, int j) {
     const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
     return __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  // both halves of m2 hold the maximum: the low half is stored as is, the high half IS the float
+  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
+    const uint32_t m = max_nan_bf16x2(max_nan_bf16x2(c.x, c.y), max_nan_bf16x2(c.z, c.w));
+    const uint32_t m2 = max_nan_bf16x2(m, __byte_perm(m, m, 0x1032));
+    packed = (uint16_t)m2;
+    cm = __uint_as_float(m2 & 0xffff0000u);
   }
   __device__ static __forceinline__ carrier pack(float m) { return (uint16_t)(__float_as_uint(m) >> 16); }
   __device__ static __forceinline__ float unpack(carrier m) { return __uint_as_float(((uint32_t)m) << 16); }
@@ -157,6 +204,12 @@ template <> struct Elem<MVGEO_F16> {
   __device__ static __forceinline__ float get(const uint4& c, int j) {
     const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
     return h2f((uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu)));
+  }
+  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
+    const uint32_t m = max_nan_f16x2(max_nan_f16x2(c.x, c.y), max_nan_f16x2(c.z, c.w));
+    const uint32_t m2 = max_nan_f16x2(m, __byte_perm(m, m, 0x1032));
+    packed = (uint16_t)m2;
+    cm = h2f(packed);
   }
   // every half is exactly representable in float and the maximum IS one of the inputs,
   // so the round trip through __float2half_rn is exact

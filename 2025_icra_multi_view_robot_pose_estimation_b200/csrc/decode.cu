@@ -20,6 +20,7 @@
 //     weight >= exp(-32) (a handful per peaked map), so no online-softmax rescaling and no
 //     exp per element in the streaming loop (MUFU would cap a bf16 stream at ~75% of HBM).
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -52,17 +53,29 @@ struct DecodeParams {
   float* kp_soft;
 };
 
+constexpr int kMaxWarps = 9;  // 8 consumer warps + 1 producer warp in the TMA kernel
+
 struct BlockScratch {
-  float val[kDecWarps];
-  int idx[kDecWarps];
-  float sum[3][kDecWarps];
+  float val[kMaxWarps];
+  int idx[kMaxWarps];
+  float sum[3][kMaxWarps];
   // per-CTA results, read by cluster peers through DSMEM
   float best_val;
   int best_idx;
   float part[3];
 };
 
-// Block-wide (value, index) arg-max. Result valid in every thread.
+// Barrier over the first NW warps of the CTA. BAR == 0 is __syncthreads() (NW must then be every
+// warp of the CTA); BAR > 0 is a named barrier, used by the persistent kernel whose producer
+// warp never takes part in the per-map reductions.
+template <int NW, int BAR>
+__device__ __forceinline__ void group_sync() {
+  if (BAR == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NW * 32) : "memory");
+}
+
+// Group-wide (value, index) arg-max. Result valid in every participating thread.
+template <int NW, int BAR>
 __device__ __forceinline__ void block_argmax(float& v, int& i, BlockScratch& s) {
   warp_argmax(v, i);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,20 +83,21 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, BlockScratch& s) 
     s.val[warp] = v;
     s.idx[warp] = i;
   }
-  __syncthreads();
+  group_sync<NW, BAR>();
   v = s.val[0];
   i = s.idx[0];
 #pragma unroll
-  for (int w = 1; w < kDecWarps; ++w) {
+  for (int w = 1; w < NW; ++w) {
     if (argmax_better(v, i, s.val[w], s.idx[w])) {
       v = s.val[w];
       i = s.idx[w];
     }
   }
-  __syncthreads();
+  group_sync<NW, BAR>();
 }
 
-// Block-wide fixed-order sums of three accumulators. Result valid in every thread.
+// Group-wide fixed-order sums of three accumulators. Result valid in every participating thread.
+template <int NW, int BAR>
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockScratch& s) {
   a = warp_sum(a);
   b = warp_sum(b);
@@ -94,15 +108,15 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockSc
     s.sum[1][warp] = b;
     s.sum[2][warp] = c;
   }
-  __syncthreads();
+  group_sync<NW, BAR>();
   a = b = c = 0.f;
 #pragma unroll
-  for (int w = 0; w < kDecWarps; ++w) {
+  for (int w = 0; w < NW; ++w) {
     a += s.sum[0][w];
     b += s.sum[1][w];
     c += s.sum[2][w];
   }
-  __syncthreads();
+  group_sync<NW, BAR>();
 }
 
 __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map, float M, int best, float s,
@@ -133,12 +147,12 @@ __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map
 }
 
 // Window soft-arg-max around (px,py): every thread takes window cells tid, tid+256, ...
-template <int DT>
+template <int DT, int NT>
 __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const void* map_base, float M, int px,
                                                   int py, float& s, float& sx, float& sy) {
   using E = Elem<DT>;
   const int r = p.radius, side = 2 * r + 1;
-  for (int t = threadIdx.x; t < side * side; t += kDecThreads) {
+  for (int t = threadIdx.x; t < side * side; t += NT) {
     const int dy = t / side - r, dx = t % side - r;
     const int y = py + dy, x = px + dx;
     if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
@@ -154,65 +168,38 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // ----------------------------------------------------------------------------------------
 // Fast path: 16-byte aligned maps whose size is a multiple of 16 bytes.
 // ----------------------------------------------------------------------------------------
+// Per-chunk work of pass 1, shared by both streaming kernels: packed max.NaN tree, 2-byte
+// st.shared of the chunk maximum (global soft mode), and the running (max, first chunk) update.
+// The maximum is canonicalised (+0.0f turns -0 into +0) so that the update test can be a plain
+// bit comparison of max.NaN results: equal values, -0/+0 and NaN/NaN all leave the FIRST chunk.
 template <int DT, int MODE>
-__global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const DecodeParams p) {
+__device__ __forceinline__ void consume_chunk(const uint4& ch, int c, typename Elem<DT>::carrier* cmax, float& run_max,
+                                              int& run_chunk) {
   using E = Elem<DT>;
-  using carrier = typename E::carrier;
+  float cm;
+  typename E::carrier packed;
+  E::chunk_max2(ch, cm, packed);
+  if (MODE == MVGEO_SOFT_GLOBAL) cmax[c] = packed;
+  const float nm = max_nan_f32(run_max, cm + 0.0f);
+  run_chunk = (__float_as_uint(nm) != __float_as_uint(run_max)) ? c : run_chunk;
+  run_max = nm;
+}
+
+// Everything after the streaming pass: resolve the first maximal element, reduce (value, index)
+// over the CTA and the cluster, run the soft-arg-max pass, write the outputs. NW warps take part
+// (barrier BAR). cmax holds the chunk maxima of this CTA's segment, padded with -inf to a multiple
+// of PER entries so that pass 2 can scan PER of them per 16-byte ld.shared.
+template <int DT, int MODE, int NW, int BAR>
+__device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScratch& sc,
+                                                const typename Elem<DT>::carrier* cmax, const uint4* mp, int64_t map,
+                                                int rank, int c_begin, int n, float run_max, int run_chunk) {
+  using E = Elem<DT>;
   constexpr int PER = E::kPerChunk;
-  __shared__ BlockScratch sc;
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  carrier* cmax = reinterpret_cast<carrier*>(dyn_smem);
-
+  constexpr int NT = NW * 32;
   const int S = p.splits;
-  const int64_t map = blockIdx.x / S;
-  const int rank = (int)(blockIdx.x - map * S);
   const int tid = threadIdx.x;
-
-  const uint4* mp = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map;
-  const int c_begin = rank * p.seg_chunks;
-  const int c_end = min(c_begin + p.seg_chunks, p.chunks_per_map);
-  const int n = max(c_end - c_begin, 0);
   const uint4* seg = mp + c_begin;
 
-  // ---------------- pass 1: stream the segment once --------------------------------------
-  float run_max = __int_as_float(0xff800000);  // -inf
-  int run_chunk = tid < n ? tid : -1;
-  constexpr int kBatch = kDecThreads * kDecUnroll;
-  const int iters = (n + kBatch - 1) / kBatch;
-
-  uint4 cur[kDecUnroll], nxt[kDecUnroll];
-#pragma unroll
-  for (int u = 0; u < kDecUnroll; ++u) {
-    const int c = u * kDecThreads + tid;
-    cur[u] = c < n ? ld_stream(seg + c) : E::neg_inf_chunk();
-  }
-  for (int it = 0; it < iters; ++it) {
-    const int base = it * kBatch;
-    if (it + 1 < iters) {
-#pragma unroll
-      for (int u = 0; u < kDecUnroll; ++u) {
-        const int c = base + kBatch + u * kDecThreads + tid;
-        nxt[u] = c < n ? ld_stream(seg + c) : E::neg_inf_chunk();
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kDecUnroll; ++u) {
-      const int c = base + u * kDecThreads + tid;
-      const float cm = E::chunk_max(cur[u]);
-      if (MODE == MVGEO_SOFT_GLOBAL) {
-        if (c < n) cmax[c] = E::pack(cm);
-      }
-      const bool gt = (cm > run_max) || ((cm != cm) && (run_max == run_max));
-      if (gt) {
-        run_max = cm;
-        run_chunk = c;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kDecUnroll; ++u) cur[u] = nxt[u];
-  }
-
-  // ---------------- resolve the first maximal element inside the winning chunk -----------
   float my_val = run_max;
   int my_idx = 0x7fffffff;
   if (run_chunk >= 0) {
@@ -225,7 +212,7 @@ __global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const Decode
       if (hit) my_idx = (c_begin + run_chunk) * PER + j;
     }
   }
-  block_argmax(my_val, my_idx, sc);
+  block_argmax<NW, BAR>(my_val, my_idx, sc);
 
   cg::cluster_group cluster = cg::this_cluster();
   if (S > 1) {
@@ -253,34 +240,42 @@ __global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const Decode
   const int best = my_idx;
   const int py = best / p.W, px = best - py * p.W;
 
-  // ---------------- pass 2: soft-arg-max sums ---------------------------------------------
   float s = 0.f, sx = 0.f, sy = 0.f;
   if (MODE == MVGEO_SOFT_GLOBAL) {
     const float thr = M - p.skip_delta;  // NaN peak: every comparison is false, nothing accumulates
-    for (int c = tid; c < n; c += kDecThreads) {
-      if (E::unpack(cmax[c]) >= thr) {
-        const uint4 ch = ld_stream(seg + c);
-        const int flat0 = (c_begin + c) * PER;
-        int y = flat0 / p.W, x = flat0 - y * p.W;
+    const uint4* cm4 = reinterpret_cast<const uint4*>(cmax);
+    const int groups = (n + PER - 1) / PER;
+    for (int g = tid; g < groups; g += NT) {
+      const uint4 cv = cm4[g];  // PER chunk maxima (carriers have the element type of the map)
+      if (E::chunk_max(cv) >= thr) {
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-          const float e = E::get(ch, j);
-          const float w = ex2_approx((e - M) * p.beta_log2e);
-          s += w;
-          sx += w * (float)(x - px);
-          sy += w * (float)(y - py);
-          if (++x == p.W) {
-            x = 0;
-            ++y;
+          const int c = g * PER + j;
+          if (c < n && E::get(cv, j) >= thr) {
+            const uint4 ch = ld_stream(seg + c);
+            const int flat0 = (c_begin + c) * PER;
+            int y = flat0 / p.W, x = flat0 - y * p.W;
+#pragma unroll
+            for (int e_ = 0; e_ < PER; ++e_) {
+              const float e = E::get(ch, e_);
+              const float w = ex2_approx((e - M) * p.beta_log2e);
+              s += w;
+              sx += w * (float)(x - px);
+              sy += w * (float)(y - py);
+              if (++x == p.W) {
+                x = 0;
+                ++y;
+              }
+            }
           }
         }
       }
     }
   } else if (MODE == MVGEO_SOFT_WINDOW) {
-    if (rank == 0) window_accumulate<DT>(p, mp, M, px, py, s, sx, sy);
+    if (rank == 0) window_accumulate<DT, NT>(p, mp, M, px, py, s, sx, sy);
   }
   if (MODE != MVGEO_SOFT_NONE) {
-    block_sum3(s, sx, sy, sc);
+    block_sum3<NW, BAR>(s, sx, sy, sc);
     if (S > 1 && MODE == MVGEO_SOFT_GLOBAL) {
       if (tid == 0) {
         sc.part[0] = s;
@@ -301,6 +296,159 @@ __global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const Decode
   }
   if (rank == 0 && tid == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
   if (S > 1) cluster.sync();  // peers' shared memory must outlive the remote reads above
+}
+
+// -inf padding of the chunk-maxima array up to a multiple of PER entries (see decode_epilogue)
+template <int DT>
+__device__ __forceinline__ void pad_cmax(typename Elem<DT>::carrier* cmax, int n) {
+  using E = Elem<DT>;
+  const int c = n + (int)threadIdx.x;
+  if ((int)threadIdx.x < E::kPerChunk && c < ((n + E::kPerChunk - 1) / E::kPerChunk) * E::kPerChunk)
+    cmax[c] = E::pack(__int_as_float(0xff800000));
+}
+
+// ---- streaming pass, variant A: register-staged ld.global.nc (kept for A/B measurements) ----
+template <int DT, int MODE>
+__global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const DecodeParams p) {
+  using E = Elem<DT>;
+  using carrier = typename E::carrier;
+  __shared__ BlockScratch sc;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  carrier* cmax = reinterpret_cast<carrier*>(dyn_smem);
+
+  const int S = p.splits;
+  const int64_t map = blockIdx.x / S;
+  const int rank = (int)(blockIdx.x - map * S);
+  const int tid = threadIdx.x;
+  const uint4* mp = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map;
+  const int c_begin = rank * p.seg_chunks;
+  const int n = max(min(c_begin + p.seg_chunks, p.chunks_per_map) - c_begin, 0);
+  const uint4* seg = mp + c_begin;
+
+  float run_max = __int_as_float(0xff800000);  // -inf
+  int run_chunk = tid < n ? tid : -1;
+  constexpr int kBatch = kDecThreads * kDecUnroll;
+  const int full = n / kBatch;
+  for (int it = 0; it < full; ++it) {
+    uint4 v[kDecUnroll];
+#pragma unroll
+    for (int u = 0; u < kDecUnroll; ++u) v[u] = ld_stream(seg + it * kBatch + u * kDecThreads + tid);
+#pragma unroll
+    for (int u = 0; u < kDecUnroll; ++u)
+      consume_chunk<DT, MODE>(v[u], it * kBatch + u * kDecThreads + tid, cmax, run_max, run_chunk);
+  }
+  for (int c = full * kBatch + tid; c < n; c += kDecThreads) {
+    const uint4 v = ld_stream(seg + c);
+    consume_chunk<DT, MODE>(v, c, cmax, run_max, run_chunk);
+  }
+  if (MODE == MVGEO_SOFT_GLOBAL) pad_cmax<DT>(cmax, n);
+  decode_epilogue<DT, MODE, kDecWarps, 0>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
+}
+
+// ---- streaming pass, variant B: TMA bulk copies into a shared-memory ring -------------------
+// One producer lane issues cp.async.bulk (SASS UBLKCP) tiles of 256*U chunks into a STAGES-deep
+// ring with full/empty mbarriers per stage; the 8 consumer warps read each tile with
+// conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by registers, and the
+// consumers carry no global address arithmetic.
+// PERSIST (maps that fit one CTA): the grid is (SMs x resident CTAs) and every CTA walks maps
+// blockIdx.x, +gridDim.x, ...; the producer keeps filling the ring with the NEXT map's tiles
+// while the consumers are in the latency-bound epilogue of the current one (they synchronise on
+// a consumer-only named barrier), so the epilogue no longer drains the memory pipeline.
+// !PERSIST (maps split over a thread-block cluster): one segment per CTA, whole CTA in the epilogue.
+template <int DT, int MODE, int U, int STAGES, bool PERSIST>
+__global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const DecodeParams p) {
+  using E = Elem<DT>;
+  using carrier = typename E::carrier;
+  constexpr int kTile = kDecThreads * U;  // chunks per tile
+  __shared__ BlockScratch sc;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  uint4* ring = reinterpret_cast<uint4*>(dyn_smem);
+  carrier* cmax = reinterpret_cast<carrier*>(dyn_smem + (size_t)STAGES * kTile * 16);
+
+  const int S = PERSIST ? 1 : p.splits;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t first = PERSIST ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / S);
+  const int64_t step = PERSIST ? (int64_t)gridDim.x : p.n_maps;  // !PERSIST: exactly one map
+  const int rank = PERSIST ? 0 : (int)(blockIdx.x - first * S);
+  const int c_begin = rank * p.seg_chunks;
+  const int n = max(min(c_begin + p.seg_chunks, p.chunks_per_map) - c_begin, 0);
+  const int n_tiles = (n + kTile - 1) / kTile;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kDecWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kDecWarps) {
+    // ------------------------------- producer ---------------------------------------------
+    if (lane == 0) {
+      int s = 0, k = 0;  // slot, and how many times the ring has wrapped
+      for (int64_t map = first; map < p.n_maps; map += step) {
+        const uint4* seg = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map + c_begin;
+        for (int t = 0; t < n_tiles; ++t) {
+          // before re-using a slot for the k-th time, wait for the consumers' (k-1)-th release of it
+          if (k > 0) mbar_wait(&empty_bar[s], (uint32_t)((k - 1) & 1));
+          const uint32_t bytes = (uint32_t)min(kTile, n - t * kTile) * 16u;
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          bulk_copy_g2s(ring + s * kTile, seg + (size_t)t * kTile, bytes, &full_bar[s]);
+          if (++s == STAGES) {
+            s = 0;
+            ++k;
+          }
+        }
+      }
+    }
+    if (PERSIST) return;  // the producer warp takes no part in the per-map reductions
+  }
+
+  // --------------------------------- consumers ---------------------------------------------
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t map = first; map < p.n_maps; map += step) {
+    const uint4* mp = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map;
+    float run_max = __int_as_float(0xff800000);  // -inf
+    int run_chunk = -1;
+    if (warp < kDecWarps) {
+      run_chunk = tid < n ? tid : -1;
+      if (MODE == MVGEO_SOFT_GLOBAL) pad_cmax<DT>(cmax, n);
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&full_bar[s], ph);
+        const uint4* tile = ring + s * kTile;
+        const int base = t * kTile;
+        if (base + kTile <= n) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = tile[u * kDecThreads + tid];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            consume_chunk<DT, MODE>(v[u], base + u * kDecThreads + tid, cmax, run_max, run_chunk);
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int c = base + u * kDecThreads + tid;
+            if (c < n) consume_chunk<DT, MODE>(tile[u * kDecThreads + tid], c, cmax, run_max, run_chunk);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    if (PERSIST)
+      decode_epilogue<DT, MODE, kDecWarps, 1>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
+    else
+      decode_epilogue<DT, MODE, kDecWarps + 1, 0>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -325,7 +473,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
       my_idx = i;
     }
   }
-  block_argmax(my_val, my_idx, sc);
+  block_argmax<kDecWarps, 0>(my_val, my_idx, sc);
   const float M = my_val;
   const int best = my_idx;
   const int py = best / p.W, px = best - py * p.W;
@@ -343,24 +491,28 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
       }
     }
   } else if (MODE == MVGEO_SOFT_WINDOW) {
-    window_accumulate<DT>(p, base, M, px, py, s, sx, sy);
+    window_accumulate<DT, kDecThreads>(p, base, M, px, py, s, sx, sy);
   }
-  if (MODE != MVGEO_SOFT_NONE) block_sum3(s, sx, sy, sc);
+  if (MODE != MVGEO_SOFT_NONE) block_sum3<kDecWarps, 0>(s, sx, sy, sc);
   if (tid == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
 }
 
-template <int DT, int MODE>
-static int launch_decode(const DecodeParams& p, bool vec, size_t smem, cudaStream_t st) {
-  if (!vec) {
-    decode_scalar_kernel<DT, MODE><<<(unsigned)p.n_maps, kDecThreads, 0, st>>>(p);
-    MVGEO_CHECK_LAUNCH();
-    return MVGEO_OK;
-  }
-  auto kern = decode_vec_kernel<DT, MODE>;
-  if (smem > 48 * 1024) MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// Streaming-kernel configuration: tile = 256*kTmaU chunks, kTmaStages-deep ring.
+#ifndef MVGEO_TMA_U
+#define MVGEO_TMA_U 2
+#endif
+#ifndef MVGEO_TMA_STAGES
+#define MVGEO_TMA_STAGES 4
+#endif
+constexpr int kTmaU = MVGEO_TMA_U;
+constexpr int kTmaStages = MVGEO_TMA_STAGES;
+
+template <typename K>
+static int launch_clustered(K kern, const DecodeParams& p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
+  if (smem > 40 * 1024) MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.n_maps * p.splits), 1, 1);
-  cfg.blockDim = dim3(kDecThreads, 1, 1);
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -374,12 +526,39 @@ static int launch_decode(const DecodeParams& p, bool vec, size_t smem, cudaStrea
   return MVGEO_OK;
 }
 
+template <int DT, int MODE>
+static int launch_decode(const DecodeParams& p, bool vec, size_t cmax_bytes, int variant, cudaStream_t st) {
+  if (!vec) {
+    decode_scalar_kernel<DT, MODE><<<(unsigned)p.n_maps, kDecThreads, 0, st>>>(p);
+    MVGEO_CHECK_LAUNCH();
+    return MVGEO_OK;
+  }
+  const unsigned one_per_segment = (unsigned)(p.n_maps * p.splits);
+  if (variant == 0)
+    return launch_clustered(decode_vec_kernel<DT, MODE>, p, one_per_segment, kDecThreads, cmax_bytes, st);
+  const size_t smem = (size_t)kTmaStages * kTmaU * kDecThreads * 16 + cmax_bytes;
+  if (p.splits > 1)
+    return launch_clustered(decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, false>, p, one_per_segment,
+                            kDecThreads + 32, smem, st);
+  // persistent: one resident wave of CTAs, each walking maps blockIdx.x, +gridDim.x, ...
+  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, true>;
+  if (smem > 40 * 1024) MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, per_sm = 0;
+  MVGEO_CUDA(cudaGetDevice(&dev));
+  MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32, smem));
+  if (per_sm < 1) return MVGEO_EUNSUPPORTED;
+  const int64_t resident = (int64_t)sms * per_sm;
+  const unsigned grid = (unsigned)(p.n_maps < resident ? p.n_maps : resident);
+  return launch_clustered(kern, p, grid, kDecThreads + 32, smem, st);
+}
+
 template <int DT>
-static int dispatch_mode(const DecodeParams& p, int mode, bool vec, size_t smem, cudaStream_t st) {
+static int dispatch_mode(const DecodeParams& p, int mode, bool vec, size_t smem, int variant, cudaStream_t st) {
   switch (mode) {
-    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, vec, 0, st);
-    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, vec, smem, st);
-    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, vec, 0, st);
+    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, vec, 0, variant, st);
+    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, vec, smem, variant, st);
+    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, vec, 0, variant, st);
   }
   return MVGEO_EINVAL;
 }
@@ -439,15 +618,19 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
     p.seg_chunks = (int)((chunks + splits - 1) / splits);
     p.splits = splits;
     if (soft_mode == MVGEO_SOFT_GLOBAL) {
-      smem = (size_t)p.seg_chunks * (dtype == MVGEO_F32 ? 4 : 2);
-      if (smem > 200 * 1024) return MVGEO_EUNSUPPORTED;  // maps beyond ~6.4 MB (f32): use the window mode
+      smem = (size_t)((p.seg_chunks + 7) / 8 * 8) * (dtype == MVGEO_F32 ? 4 : 2);  // padded for the 16-byte scan
+      if (smem > 150 * 1024) return MVGEO_EUNSUPPORTED;  // maps beyond ~6.4 MB (f32): use the window mode
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // A/B switch for kernel development only (MVGEO_DECODE_VARIANT=0 selects the register-staged
+  // ld.global variant); both variants produce bit-identical results.
+  const char* ev = getenv("MVGEO_DECODE_VARIANT");
+  const int variant = (ev && ev[0] == '0') ? 0 : 1;
   switch (dtype) {
-    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, smem, st);
-    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, vec, smem, st);
-    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, vec, smem, st);
+    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, smem, variant, st);
+    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, vec, smem, variant, st);
+    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, vec, smem, variant, st);
   }
   return MVGEO_EINVAL;
 }

@@ -38,13 +38,13 @@ __device__ __forceinline__ float dot(const Vec3& a, const Vec3& b) { return a.x 
 // Serial DH chain in the base frame. pts[0..K) are the emitted points; when AXES, axis[i] /
 // apt[i] describe joint i for the backward and first_pt[i] is the first emitted point that
 // moves with joint i.
-template <bool AXES>
+template <bool AXES, bool BASE>
 __device__ __forceinline__ void chain_forward(const mvgeo_chain& ch, const float* __restrict__ q, Vec3* pts,
                                               Vec3* axis, Vec3* apt) {
-  // T = [r0 r1 r2 | p], columns of the rotation kept as three vectors
+  // T = [r0 r1 r2 | p], columns of the rotation kept as three vectors. BASE (= emit_base) is a
+  // template parameter so that every pts[] index is a compile-time constant (registers, no stack).
   Vec3 cx = {1.f, 0.f, 0.f}, cy = {0.f, 1.f, 0.f}, cz = {0.f, 0.f, 1.f}, p = {0.f, 0.f, 0.f};
-  int k = 0;
-  if (ch.emit_base) pts[k++] = p;
+  if (BASE) pts[0] = p;
 #pragma unroll
   for (int i = 0; i < MVGEO_MAX_JOINTS; ++i) {
     if (i < ch.n_joints) {
@@ -81,7 +81,7 @@ __device__ __forceinline__ void chain_forward(const mvgeo_chain& ch, const float
           apt[i] = p;
         }
       }
-      pts[k++] = p;
+      pts[i + (BASE ? 1 : 0)] = p;
     }
   }
 }
@@ -154,14 +154,15 @@ __device__ __forceinline__ void project_point(const CamRegs& c, const Vec3& X, f
 }
 
 // ------------------------------------------------------------------------------ kernels
+template <bool BASE>
 __global__ void __launch_bounds__(kFkThreads) fk_kernel(const mvgeo_chain ch, const float* __restrict__ q, int64_t B,
                                                         const float* __restrict__ R_view, int V,
                                                         float* __restrict__ X) {
   const int64_t b = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
   if (b >= B) return;
   Vec3 pts[kMaxPts];
-  chain_forward<false>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
-  const int K = ch.n_joints + (ch.emit_base ? 1 : 0);
+  chain_forward<false, BASE>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
+  const int K = ch.n_joints + (BASE ? 1 : 0);
   for (int v = 0; v < V; ++v) {
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     if (R_view) {
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kFkThreads) project_kernel(const float* __rest
   uv[2 * i + 1] = w;
 }
 
+template <bool BASE>
 __global__ void __launch_bounds__(kFkThreads)
     fk_reproj_fwd_kernel(const mvgeo_chain ch, const float* __restrict__ q, int64_t B,
                          const float* __restrict__ R_view, const mvgeo_camera* __restrict__ cams, int V,
@@ -205,8 +207,8 @@ __global__ void __launch_bounds__(kFkThreads)
   const int64_t b = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
   if (b >= B) return;
   Vec3 pts[kMaxPts];
-  chain_forward<false>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
-  const int K = ch.n_joints + (ch.emit_base ? 1 : 0);
+  chain_forward<false, BASE>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
+  const int K = ch.n_joints + (BASE ? 1 : 0);
   float acc = 0.f;
   for (int v = 0; v < V; ++v) {
     const CamRegs c = load_cam(cams, R_view, v);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(kFkThreads)
   if (frame_loss) frame_loss[b] = acc * scale;
 }
 
+template <bool BASE>
 __global__ void __launch_bounds__(kFkThreads)
     fk_reproj_bwd_kernel(const mvgeo_chain ch, const float* __restrict__ q, int64_t B,
                          const float* __restrict__ R_view, const mvgeo_camera* __restrict__ cams, int V,
@@ -253,8 +256,8 @@ __global__ void __launch_bounds__(kFkThreads)
   const int64_t b = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
   if (b >= B) return;
   Vec3 pts[kMaxPts], axis[MVGEO_MAX_JOINTS], apt[MVGEO_MAX_JOINTS];
-  chain_forward<true>(ch, q + b * ch.n_joints, pts, axis, apt);
-  const int K = ch.n_joints + (ch.emit_base ? 1 : 0);
+  chain_forward<true, BASE>(ch, q + b * ch.n_joints, pts, axis, apt);
+  const int K = ch.n_joints + (BASE ? 1 : 0);
   const float up = (dloss ? dloss[0] : 1.0f) * scale * 2.0f;
   Vec3 g[kMaxPts];
 #pragma unroll
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kFkThreads)
   }
   // suffix sums from the end of the chain; point index of joint i is i + emit_base
   Vec3 G = {0.f, 0.f, 0.f}, N = {0.f, 0.f, 0.f};
-  const int off = ch.emit_base ? 1 : 0;
+  constexpr int off = BASE ? 1 : 0;
 #pragma unroll
   for (int i = MVGEO_MAX_JOINTS - 1; i >= 0; --i) {
     if (i < ch.n_joints) {
@@ -379,7 +382,9 @@ extern "C" int mvgeo_fk(const mvgeo_chain* chain, const float* q, int64_t B, con
   if (B == 0) return MVGEO_OK;
   if (!q || !X) return MVGEO_ENULL;
   const unsigned grid = (unsigned)((B + kFkThreads - 1) / kFkThreads);
-  fk_kernel<<<grid, kFkThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*chain, q, B, R_view, V, X);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (chain->emit_base) fk_kernel<true><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, V, X);
+  else fk_kernel<false><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, V, X);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }
@@ -410,8 +415,12 @@ extern "C" int mvgeo_fk_reproj_fwd(const mvgeo_chain* chain, const float* q, int
   const float scale = (float)((double)lambda / ((double)B * V * K * 2.0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((B + kFkThreads - 1) / kFkThreads);
-  fk_reproj_fwd_kernel<<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out, uv_out,
-                                                    frame_loss);
+  if (chain->emit_base)
+    fk_reproj_fwd_kernel<true><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
+                                                            uv_out, frame_loss);
+  else
+    fk_reproj_fwd_kernel<false><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
+                                                             uv_out, frame_loss);
   MVGEO_CHECK_LAUNCH();
   if (loss) return launch_sum(frame_loss, B, loss, st);
   return MVGEO_OK;
@@ -428,8 +437,11 @@ extern "C" int mvgeo_fk_reproj_bwd(const mvgeo_chain* chain, const float* q, int
   const int K = chain->n_joints + (chain->emit_base ? 1 : 0);
   const float scale = (float)((double)lambda / ((double)B * V * K * 2.0));
   const unsigned grid = (unsigned)((B + kFkThreads - 1) / kFkThreads);
-  fk_reproj_bwd_kernel<<<grid, kFkThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (chain->emit_base)
+    fk_reproj_bwd_kernel<true><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
+  else
+    fk_reproj_bwd_kernel<false><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }

@@ -80,12 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "MVGEO_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra MVGEO_DONE_%=;\n"
       "bra MVGEO_WAIT_%=;\n"
       "MVGEO_DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of re-polling
       : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0).

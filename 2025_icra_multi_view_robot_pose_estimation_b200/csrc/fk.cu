@@ -198,19 +198,25 @@ __global__ void __launch_bounds__(kFkThreads) project_kernel(const float* __rest
   uv[2 * i + 1] = w;
 }
 
+// One thread per (frame, view): the chain is recomputed per view (J sincos, cheap) so that a
+// small batch still fills the machine and the serial projection loop is K points, not V*K.
+// blockDim.x = frames_per_cta * V; the per-frame sums over views go through shared memory in
+// fixed view order (deterministic, no atomics).
 template <bool BASE>
 __global__ void __launch_bounds__(kFkThreads)
     fk_reproj_fwd_kernel(const mvgeo_chain ch, const float* __restrict__ q, int64_t B,
                          const float* __restrict__ R_view, const mvgeo_camera* __restrict__ cams, int V,
                          const float* __restrict__ gt_uv, const float* __restrict__ w, float scale,
                          float* __restrict__ X_out, float* __restrict__ uv_out, float* __restrict__ frame_loss) {
-  const int64_t b = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
-  if (b >= B) return;
-  Vec3 pts[kMaxPts];
-  chain_forward<false, BASE>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
-  const int K = ch.n_joints + (BASE ? 1 : 0);
+  __shared__ float part[kFkThreads];
+  const int fpc = blockDim.x / V;
+  const int fl = threadIdx.x / V, v = threadIdx.x - fl * V;
+  const int64_t b = (int64_t)blockIdx.x * fpc + fl;
   float acc = 0.f;
-  for (int v = 0; v < V; ++v) {
+  if (b < B) {
+    Vec3 pts[kMaxPts];
+    chain_forward<false, BASE>(ch, q + b * ch.n_joints, pts, nullptr, nullptr);
+    const int K = ch.n_joints + (BASE ? 1 : 0);
     const CamRegs c = load_cam(cams, R_view, v);
     const int64_t base = (b * V + v) * K;
     float Rv[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
@@ -244,7 +250,15 @@ __global__ void __launch_bounds__(kFkThreads)
       }
     }
   }
-  if (frame_loss) frame_loss[b] = acc * scale;
+  if (frame_loss) {
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (b < B && v == 0) {
+      float t = 0.f;
+      for (int i = 0; i < V; ++i) t += part[fl * V + i];
+      frame_loss[b] = t * scale;
+    }
+  }
 }
 
 template <bool BASE>
@@ -253,47 +267,54 @@ __global__ void __launch_bounds__(kFkThreads)
                          const float* __restrict__ R_view, const mvgeo_camera* __restrict__ cams, int V,
                          const float* __restrict__ gt_uv, const float* __restrict__ w, float scale,
                          const float* __restrict__ dloss, float* __restrict__ dq) {
-  const int64_t b = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
-  if (b >= B) return;
-  Vec3 pts[kMaxPts], axis[MVGEO_MAX_JOINTS], apt[MVGEO_MAX_JOINTS];
-  chain_forward<true, BASE>(ch, q + b * ch.n_joints, pts, axis, apt);
-  const int K = ch.n_joints + (BASE ? 1 : 0);
-  const float up = (dloss ? dloss[0] : 1.0f) * scale * 2.0f;
-  Vec3 g[kMaxPts];
+  __shared__ float part[kFkThreads][MVGEO_MAX_JOINTS];
+  const int fpc = blockDim.x / V;
+  const int fl = threadIdx.x / V, v = threadIdx.x - fl * V;
+  const int64_t b = (int64_t)blockIdx.x * fpc + fl;
+  float dqv[MVGEO_MAX_JOINTS];
 #pragma unroll
-  for (int k = 0; k < kMaxPts; ++k) g[k] = {0.f, 0.f, 0.f};
-  for (int v = 0; v < V; ++v) {
+  for (int i = 0; i < MVGEO_MAX_JOINTS; ++i) dqv[i] = 0.f;
+  if (b < B) {
+    Vec3 pts[kMaxPts], axis[MVGEO_MAX_JOINTS], apt[MVGEO_MAX_JOINTS];
+    chain_forward<true, BASE>(ch, q + b * ch.n_joints, pts, axis, apt);
+    const int K = ch.n_joints + (BASE ? 1 : 0);
+    const float up = (dloss ? dloss[0] : 1.0f) * scale * 2.0f;
     const CamRegs c = load_cam(cams, R_view, v);
     const int64_t base = (b * V + v) * K;
+    // suffix sums from the end of the chain; point index of joint i is i + emit_base
+    Vec3 G = {0.f, 0.f, 0.f}, N = {0.f, 0.f, 0.f};
+    constexpr int off = BASE ? 1 : 0;
 #pragma unroll
-    for (int k = 0; k < kMaxPts; ++k) {
-      if (k < K) {
+    for (int i = MVGEO_MAX_JOINTS - 1; i >= 0; --i) {
+      if (i < ch.n_joints) {
+        const int k = i + off;
+        Vec3 g = {0.f, 0.f, 0.f};
         const float gu = gt_uv[2 * (base + k)], gv = gt_uv[2 * (base + k) + 1];
         if (isfinite(gu) && isfinite(gv)) {
           float u, vv, J[6];
           project_point<true>(c, pts[k], u, vv, J);
           const float wt = (w ? w[base + k] : 1.0f) * up;
           const float ru = wt * (u - gu), rv = wt * (vv - gv);
-          g[k].x += ru * J[0] + rv * J[3];
-          g[k].y += ru * J[1] + rv * J[4];
-          g[k].z += ru * J[2] + rv * J[5];
+          g = {ru * J[0] + rv * J[3], ru * J[1] + rv * J[4], ru * J[2] + rv * J[5]};
         }
+        G = {G.x + g.x, G.y + g.y, G.z + g.z};
+        const Vec3 pxg = cross(pts[k], g);
+        N = {N.x + pxg.x, N.y + pxg.y, N.z + pxg.z};
+        const Vec3 oxG = cross(apt[i], G);
+        const Vec3 m = {N.x - oxG.x, N.y - oxG.y, N.z - oxG.z};
+        dqv[i] = dot(axis[i], m) * ch.angle_scale;
       }
     }
   }
-  // suffix sums from the end of the chain; point index of joint i is i + emit_base
-  Vec3 G = {0.f, 0.f, 0.f}, N = {0.f, 0.f, 0.f};
-  constexpr int off = BASE ? 1 : 0;
 #pragma unroll
-  for (int i = MVGEO_MAX_JOINTS - 1; i >= 0; --i) {
-    if (i < ch.n_joints) {
-      const int k = i + off;
-      G = {G.x + g[k].x, G.y + g[k].y, G.z + g[k].z};
-      const Vec3 pxg = cross(pts[k], g[k]);
-      N = {N.x + pxg.x, N.y + pxg.y, N.z + pxg.z};
-      const Vec3 oxG = cross(apt[i], G);
-      const Vec3 m = {N.x - oxG.x, N.y - oxG.y, N.z - oxG.z};
-      dq[b * ch.n_joints + i] = dot(axis[i], m) * ch.angle_scale;
+  for (int i = 0; i < MVGEO_MAX_JOINTS; ++i) part[threadIdx.x][i] = dqv[i];
+  __syncthreads();
+  // threads (fl, j) with j < n_joints add the V per-view partials of joint j in fixed order
+  for (int j = v; j < ch.n_joints; j += V) {
+    if (b < B) {
+      float t = 0.f;
+      for (int i = 0; i < V; ++i) t += part[fl * V + i][j];
+      dq[b * ch.n_joints + j] = t;
     }
   }
 }
@@ -414,12 +435,13 @@ extern "C" int mvgeo_fk_reproj_fwd(const mvgeo_chain* chain, const float* q, int
   const int K = chain->n_joints + (chain->emit_base ? 1 : 0);
   const float scale = (float)((double)lambda / ((double)B * V * K * 2.0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((B + kFkThreads - 1) / kFkThreads);
+  const int fpc = kFkThreads / V;  // V <= 16, so at least 8 frames per CTA
+  const unsigned grid = (unsigned)((B + fpc - 1) / fpc);
   if (chain->emit_base)
-    fk_reproj_fwd_kernel<true><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
+    fk_reproj_fwd_kernel<true><<<grid, fpc * V, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
                                                             uv_out, frame_loss);
   else
-    fk_reproj_fwd_kernel<false><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
+    fk_reproj_fwd_kernel<false><<<grid, fpc * V, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, X_out,
                                                              uv_out, frame_loss);
   MVGEO_CHECK_LAUNCH();
   if (loss) return launch_sum(frame_loss, B, loss, st);
@@ -436,12 +458,13 @@ extern "C" int mvgeo_fk_reproj_bwd(const mvgeo_chain* chain, const float* q, int
   if (!q || !cams || !gt_uv || !dq) return MVGEO_ENULL;
   const int K = chain->n_joints + (chain->emit_base ? 1 : 0);
   const float scale = (float)((double)lambda / ((double)B * V * K * 2.0));
-  const unsigned grid = (unsigned)((B + kFkThreads - 1) / kFkThreads);
+  const int fpc = kFkThreads / V;
+  const unsigned grid = (unsigned)((B + fpc - 1) / fpc);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (chain->emit_base)
-    fk_reproj_bwd_kernel<true><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
+    fk_reproj_bwd_kernel<true><<<grid, fpc * V, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
   else
-    fk_reproj_bwd_kernel<false><<<grid, kFkThreads, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
+    fk_reproj_bwd_kernel<false><<<grid, fpc * V, 0, st>>>(*chain, q, B, R_view, cams, V, gt_uv, w, scale, dloss, dq);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }

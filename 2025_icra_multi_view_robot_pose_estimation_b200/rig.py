@@ -117,6 +117,17 @@ class CameraRig:
             ts.append(-Rm @ c)
         return CameraRig(np.array(K), np.array(D), np.array(Rs), np.array(ts))
 
+    #: ring placement that keeps the whole arm in view, in the (view-rotated) frame the robot's FK
+    #: emits: FR3's base correction flips z (model/MvRoPose_FR3.py:105-110), so its workspace is z < 0
+    _RING_FOR = {"fr3": dict(radius=2.2, height=-1.2, target=(0.0, 0.0, -0.45)),
+                 "fr5": dict(radius=2.4, height=0.6, target=(0.0, 0.0, 0.0)),
+                 "meca500": dict(radius=0.9, height=0.5, target=(0.0, 0.0, 0.2))}
+
+    @staticmethod
+    def synthetic_ring_for(robot: str, n_views: int, distortion: bool = False) -> "CameraRig":
+        """synthetic_ring aimed at `robot`'s workspace (closed-loop benchmarks and examples)."""
+        return CameraRig.synthetic_ring(n_views, distortion=distortion, **CameraRig._RING_FOR[robot.lower()])
+
     def packed(self) -> np.ndarray:
         """(V,24) float32 rows laid out as mvgeo_camera (include/mvgeo.h)."""
         V = self.n_views

@@ -46,3 +46,47 @@ def gather_frames(local: Dict[str, torch.Tensor], n_frames: int, group=None) -> 
         parts = [buf[r * cap: r * cap + counts[r]] for r in range(ws)]
         out[name] = torch.cat(parts, dim=0) if any(c != cap for c in counts) else buf
     return out
+
+
+class PackedResults:
+    """Per-frame result tensors laid out back to back in ONE flat device buffer, so the final
+    gather is a single all_gather_into_tensor however many result arrays there are (launch
+    latency, not bytes, is what a ~1 MB gather costs on NVSwitch). Every entry is a dense,
+    contiguous view the kernels can write straight into.
+
+        pr = PackedResults({"X_tri": ((B, K, 3), torch.float32), "score": ((B, V, K), torch.float32)}, device)
+        kernel(..., pr["X_tri"].data_ptr(), ...)
+        full = pr.all_gather()          # {"X_tri": (world, B, K, 3), ...}: views, no copy
+    Requires the same frame count on every rank (weak-scaling batches)."""
+
+    def __init__(self, spec: Dict[str, tuple], device):
+        self._spec, self._views, off = {}, {}, 0
+        for name, (shape, dtype) in spec.items():
+            if torch.empty((), dtype=dtype).element_size() != 4:
+                raise ValueError("PackedResults holds 32-bit types only")
+            n = 1
+            for d in shape:
+                n *= int(d)
+            self._spec[name] = (off, n, tuple(shape), dtype)
+            off += n
+        self.flat = torch.empty((off,), dtype=torch.float32, device=device)
+        for name, (o, n, shape, dtype) in self._spec.items():
+            self._views[name] = self.flat[o:o + n].view(dtype).view(shape)
+        self._gathered = None
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self._views[name]
+
+    def keys(self):
+        return self._views.keys()
+
+    def all_gather(self, group=None) -> Dict[str, torch.Tensor]:
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return {k: v.unsqueeze(0) for k, v in self._views.items()}
+        ws = dist.get_world_size(group)
+        if self._gathered is None or self._gathered.numel() != ws * self.flat.numel():
+            self._gathered = self.flat.new_empty((ws * self.flat.numel(),))  # concatenated form (gloo and nccl)
+        dist.all_gather_into_tensor(self._gathered, self.flat, group=group)
+        g2 = self._gathered.view(ws, self.flat.numel())
+        return {name: g2[:, o:o + n].view(dtype).view((ws,) + shape)
+                for name, (o, n, shape, dtype) in self._spec.items()}

@@ -187,6 +187,13 @@ out = mvgeo.sharding.gather_frames(local, n)
 assert set(out) == {{"X", "idx"}}
 for k in full:
     assert torch.equal(out[k], full[k]), k
+pr = mvgeo.sharding.PackedResults({{"X": ((3, 2), torch.float32), "i": ((3,), torch.int32)}}, "cpu")
+pr["X"].copy_(torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * rank); pr["i"].copy_(torch.arange(3, dtype=torch.int32) - rank)
+g = pr.all_gather()
+assert g["X"].shape == (2, 3, 2) and g["i"].shape == (2, 3) and g["i"].dtype == torch.int32
+for r in range(ws):
+    assert torch.equal(g["X"][r], torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * r)
+    assert torch.equal(g["i"][r], torch.arange(3, dtype=torch.int32) - r)
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """

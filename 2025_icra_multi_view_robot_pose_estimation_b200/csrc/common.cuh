@@ -142,11 +142,13 @@ template <> struct Elem<MVGEO_F32> {
     const uint32_t w = j == 0 ? c.x : j == 1 ? c.y : j == 2 ? c.z : c.w;
     return __uint_as_float(w);
   }
-  // chunk maximum both as a float and in its shared-memory carrier form
-  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
-    cm = chunk_max(c);
-    packed = cm;
+  // "vertical" maximum of a chunk kept in a 32-bit register (for f32 simply the chunk maximum),
+  // merge of two such values, and the final horizontal step giving the float maximum
+  __device__ static __forceinline__ uint32_t vmax(const uint4& c) { return __float_as_uint(chunk_max(c)); }
+  __device__ static __forceinline__ uint32_t vmerge(uint32_t a, uint32_t b) {
+    return __float_as_uint(max_nan_f32(__uint_as_float(a), __uint_as_float(b)));
   }
+  __device__ static __forceinline__ float vfinish(uint32_t v) { return __uint_as_float(v); }
   __device__ static __forceinline__ carrier pack(float m) { return m; }
   __device__ static __forceinline__ float unpack(carrier m) { return m; }
   __device__ static __forceinline__ float load(const void* base, int64_t i) {
@@ -172,12 +174,15 @@ template <> struct Elem<MVGEO_BF16> {
     const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
     return __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
   }
-  // both halves of m2 hold the maximum: the low half is stored as is, the high half IS the float
-  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
-    const uint32_t m = max_nan_bf16x2(max_nan_bf16x2(c.x, c.y), max_nan_bf16x2(c.z, c.w));
-    const uint32_t m2 = max_nan_bf16x2(m, __byte_perm(m, m, 0x1032));
-    packed = (uint16_t)m2;
-    cm = __uint_as_float(m2 & 0xffff0000u);
+  // packed bf16x2 "vertical" maximum (2 SIMD instructions per chunk); the horizontal step is
+  // done once per slice: after it both halves hold the maximum and the high half IS the float
+  __device__ static __forceinline__ uint32_t vmax(const uint4& c) {
+    return max_nan_bf16x2(max_nan_bf16x2(c.x, c.y), max_nan_bf16x2(c.z, c.w));
+  }
+  __device__ static __forceinline__ uint32_t vmerge(uint32_t a, uint32_t b) { return max_nan_bf16x2(a, b); }
+  __device__ static __forceinline__ float vfinish(uint32_t v) {
+    const uint32_t m2 = max_nan_bf16x2(v, __byte_perm(v, v, 0x1032));
+    return __uint_as_float(m2 & 0xffff0000u);
   }
   __device__ static __forceinline__ carrier pack(float m) { return (uint16_t)(__float_as_uint(m) >> 16); }
   __device__ static __forceinline__ float unpack(carrier m) { return __uint_as_float(((uint32_t)m) << 16); }
@@ -205,11 +210,13 @@ template <> struct Elem<MVGEO_F16> {
     const uint32_t w = (j >> 1) == 0 ? c.x : (j >> 1) == 1 ? c.y : (j >> 1) == 2 ? c.z : c.w;
     return h2f((uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu)));
   }
-  __device__ static __forceinline__ void chunk_max2(const uint4& c, float& cm, carrier& packed) {
-    const uint32_t m = max_nan_f16x2(max_nan_f16x2(c.x, c.y), max_nan_f16x2(c.z, c.w));
-    const uint32_t m2 = max_nan_f16x2(m, __byte_perm(m, m, 0x1032));
-    packed = (uint16_t)m2;
-    cm = h2f(packed);
+  __device__ static __forceinline__ uint32_t vmax(const uint4& c) {
+    return max_nan_f16x2(max_nan_f16x2(c.x, c.y), max_nan_f16x2(c.z, c.w));
+  }
+  __device__ static __forceinline__ uint32_t vmerge(uint32_t a, uint32_t b) { return max_nan_f16x2(a, b); }
+  __device__ static __forceinline__ float vfinish(uint32_t v) {
+    const uint32_t m2 = max_nan_f16x2(v, __byte_perm(v, v, 0x1032));
+    return h2f((uint16_t)m2);
   }
   // every half is exactly representable in float and the maximum IS one of the inputs,
   // so the round trip through __float2half_rn is exact

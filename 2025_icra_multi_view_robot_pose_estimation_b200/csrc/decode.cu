@@ -6,19 +6,25 @@
 //
 // Roofline: HBM. Every map byte is read from DRAM exactly once (algorithmic bytes per map =
 // H*W*sizeof(dtype); outputs are 28 B per map). Design:
-//   * one CTA (or one thread-block cluster of S CTAs for maps > 192 KB) per map; each thread
-//     streams 16-byte vectors with ld.global.nc.L1::no_allocate, 2 x 4 loads in flight
-//     (software-pipelined batches), 4 CTAs / SM -> ~128 KB in flight per SM;
+//   * PERSISTENT kernel: (SMs x resident CTAs) CTAs, each walking maps blockIdx.x, +gridDim.x, ...
+//     One producer lane per CTA issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of 8 KB
+//     tiles into a 4-stage shared-memory ring with full/empty mbarriers; 8 consumer warps read
+//     the tiles with conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by
+//     registers, and the producer keeps prefetching the NEXT map while the consumers are in the
+//     latency-bound per-map epilogue (consumer-only named barrier), so the DRAM pipe never drains;
 //   * pass 1 does the minimum ALU work per byte: a packed max.NaN tree per 16-byte chunk
-//     (bf16x2 / f16x2 SIMD for 16-bit maps), one scalar (max, first-chunk) update per chunk,
-//     and (global soft mode only) one 2-byte st.shared of the chunk maximum;
+//     (bf16x2 / f16x2 SIMD for 16-bit maps), one (max, first-chunk) update per chunk, and (global
+//     soft mode only) one 2-byte st.shared per thread per tile of the tile-slice maximum;
 //   * the arg-max index is resolved afterwards by re-reading ONE chunk per thread, then a
-//     warp-shuffle / shared-memory / DSMEM (value, index) reduction with torch.argmax's
+//     warp-shuffle / shared-memory (/ DSMEM) (value, index) reduction with torch.argmax's
 //     first-maximum, NaN-is-maximal ordering;
-//   * pass 2 (soft-arg-max) is exact with respect to the TRUE map maximum: threads scan
-//     their chunk maxima in shared memory and re-read from L2 only chunks that can carry a
-//     weight >= exp(-32) (a handful per peaked map), so no online-softmax rescaling and no
-//     exp per element in the streaming loop (MUFU would cap a bf16 stream at ~75% of HBM).
+//   * pass 2 (soft-arg-max) is exact with respect to the TRUE map maximum: threads scan the
+//     slice maxima in shared memory, 8 per ld.shared.v4, and re-read from L2 only slices that can
+//     carry a weight >= exp(-32) (a handful per peaked map), so there is no online-softmax
+//     rescaling and no exp per element in the streaming loop (MUFU would cap a bf16 stream at
+//     ~75% of HBM). A flat map (nothing can be skipped) re-reads itself: bounded 2x, data-dependent;
+//   * maps whose slice-maxima table cannot fit one CTA (> ~2.4 MB) are split over a thread-block
+//     cluster of <= 8 CTAs and combined through distributed shared memory.
 #include <cooperative_groups.h>
 #include <cstdlib>
 
@@ -30,7 +36,6 @@ namespace mvgeo {
 
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kDecUnroll = 4;
 constexpr int kMaxSplits = 8;  // portable cluster size
 
 struct DecodeParams {
@@ -65,25 +70,31 @@ struct BlockScratch {
   float part[3];
 };
 
-// Barrier over the first NW warps of the CTA. BAR == 0 is __syncthreads() (NW must then be every
-// warp of the CTA); BAR > 0 is a named barrier, used by the persistent kernel whose producer
-// warp never takes part in the per-map reductions.
-template <int NW, int BAR>
-__device__ __forceinline__ void group_sync() {
-  if (BAR == 0) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NW * 32) : "memory");
+// Barrier over a group of NW warps. bar == 0 is __syncthreads() (the group must then be the whole
+// CTA); bar > 0 is a named barrier, used by the persistent kernel whose consumer warp groups
+// reduce independently of one another and of the producer warp.
+template <int NW>
+__device__ __forceinline__ void group_sync(int bar) {
+  // literal barrier ids so that ptxas reserves 5 hardware barriers per CTA, not all 16
+  switch (bar) {
+    case 0: __syncthreads(); break;
+    case 1: asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); break;
+    case 2: asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory"); break;
+    case 3: asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory"); break;
+  }
 }
 
-// Group-wide (value, index) arg-max. Result valid in every participating thread.
-template <int NW, int BAR>
-__device__ __forceinline__ void block_argmax(float& v, int& i, BlockScratch& s) {
+// Group-wide (value, index) arg-max; `lw` is the warp's index inside the group. Result valid in
+// every participating thread.
+template <int NW>
+__device__ __forceinline__ void block_argmax(float& v, int& i, BlockScratch& s, int bar, int lw) {
   warp_argmax(v, i);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    s.val[warp] = v;
-    s.idx[warp] = i;
+  if ((threadIdx.x & 31) == 0) {
+    s.val[lw] = v;
+    s.idx[lw] = i;
   }
-  group_sync<NW, BAR>();
+  group_sync<NW>(bar);
   v = s.val[0];
   i = s.idx[0];
 #pragma unroll
@@ -93,22 +104,21 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, BlockScratch& s) 
       i = s.idx[w];
     }
   }
-  group_sync<NW, BAR>();
+  group_sync<NW>(bar);
 }
 
 // Group-wide fixed-order sums of three accumulators. Result valid in every participating thread.
-template <int NW, int BAR>
-__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockScratch& s) {
+template <int NW>
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockScratch& s, int bar, int lw) {
   a = warp_sum(a);
   b = warp_sum(b);
   c = warp_sum(c);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    s.sum[0][warp] = a;
-    s.sum[1][warp] = b;
-    s.sum[2][warp] = c;
+  if ((threadIdx.x & 31) == 0) {
+    s.sum[0][lw] = a;
+    s.sum[1][lw] = b;
+    s.sum[2][lw] = c;
   }
-  group_sync<NW, BAR>();
+  group_sync<NW>(bar);
   a = b = c = 0.f;
 #pragma unroll
   for (int w = 0; w < NW; ++w) {
@@ -116,7 +126,7 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockSc
     b += s.sum[1][w];
     c += s.sum[2][w];
   }
-  group_sync<NW, BAR>();
+  group_sync<NW>(bar);
 }
 
 __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map, float M, int best, float s,
@@ -149,10 +159,10 @@ __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map
 // Window soft-arg-max around (px,py): every thread takes window cells tid, tid+256, ...
 template <int DT, int NT>
 __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const void* map_base, float M, int px,
-                                                  int py, float& s, float& sx, float& sy) {
+                                                  int py, int t0, float& s, float& sx, float& sy) {
   using E = Elem<DT>;
   const int r = p.radius, side = 2 * r + 1;
-  for (int t = threadIdx.x; t < side * side; t += NT) {
+  for (int t = t0; t < side * side; t += NT) {
     const int dy = t / side - r, dx = t % side - r;
     const int y = py + dy, x = px + dx;
     if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
@@ -168,55 +178,58 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // ----------------------------------------------------------------------------------------
 // Fast path: 16-byte aligned maps whose size is a multiple of 16 bytes.
 // ----------------------------------------------------------------------------------------
-// Per-chunk work of pass 1, shared by both streaming kernels: packed max.NaN tree, 2-byte
-// st.shared of the chunk maximum (global soft mode), and the running (max, first chunk) update.
-// The maximum is canonicalised (+0.0f turns -0 into +0) so that the update test can be a plain
-// bit comparison of max.NaN results: equal values, -0/+0 and NaN/NaN all leave the FIRST chunk.
-template <int DT, int MODE>
-__device__ __forceinline__ void consume_chunk(const uint4& ch, int c, typename Elem<DT>::carrier* cmax, float& run_max,
-                                              int& run_chunk) {
-  using E = Elem<DT>;
-  float cm;
-  typename E::carrier packed;
-  E::chunk_max2(ch, cm, packed);
-  if (MODE == MVGEO_SOFT_GLOBAL) cmax[c] = packed;
-  const float nm = max_nan_f32(run_max, cm + 0.0f);
-  run_chunk = (__float_as_uint(nm) != __float_as_uint(run_max)) ? c : run_chunk;
-  run_max = nm;
+// A "slice" is the U chunks {(t*U + u)*NT + gtid, u < U} that one consumer thread owns in tile t.
+// Slice maxima ("carriers") are 16-bit: the map's own type for bf16 / f16 maps (exact), bf16
+// rounded UP for f32 maps (a conservative filter: a slice is re-read whenever it might matter,
+// and every re-read element is weighted exactly).
+template <int DT> struct Carrier { using E = Elem<DT>; };
+template <> struct Carrier<MVGEO_F32> { using E = Elem<MVGEO_BF16>; };
+
+template <int DT>
+__device__ __forceinline__ uint16_t to_carrier(float m) {
+  if (DT == MVGEO_F32) return __bfloat16_as_ushort(__float2bfloat16_ru(m));
+  return Elem<DT>::pack(m);
 }
 
-// Everything after the streaming pass: resolve the first maximal element, reduce (value, index)
-// over the CTA and the cluster, run the soft-arg-max pass, write the outputs. NW warps take part
-// (barrier BAR). cmax holds the chunk maxima of this CTA's segment, padded with -inf to a multiple
-// of PER entries so that pass 2 can scan PER of them per 16-byte ld.shared.
-template <int DT, int MODE, int NW, int BAR>
-__device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScratch& sc,
-                                                const typename Elem<DT>::carrier* cmax, const uint4* mp, int64_t map,
-                                                int rank, int c_begin, int n, float run_max, int run_chunk) {
+// Everything after the streaming pass, for one group of NW consumer warps (NT = 32 NW threads,
+// barrier `bar`, `gt` = thread index in the group): resolve the first maximal element inside the
+// winning slice, reduce (value, index) over the group and the cluster, run the soft-arg-max
+// pass, write the outputs. smax[t*NT + gt] = maximum of thread gt's slice of tile t.
+template <int DT, int MODE, int NW, int U>
+__device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScratch& sc, const uint16_t* smax,
+                                                const uint4* mp, int64_t map, int rank, int c_begin, int n,
+                                                int n_tiles, float run_max, int run_tile, const uint4 (&run_v)[U],
+                                                int bar, int gt) {
   using E = Elem<DT>;
+  using CE = typename Carrier<DT>::E;
   constexpr int PER = E::kPerChunk;
   constexpr int NT = NW * 32;
   const int S = p.splits;
-  const int tid = threadIdx.x;
+  const int lw = gt >> 5;
   const uint4* seg = mp + c_begin;
 
+  // first maximal element inside the winning slice, straight from the registers that kept it
+  // (no global re-read on the latency-critical path). Descending loops: the lowest index sticks.
   float my_val = run_max;
   int my_idx = 0x7fffffff;
-  if (run_chunk >= 0) {
-    const uint4 ch = ld_stream(seg + run_chunk);
+  if (run_tile >= 0) {
     const bool isn = (run_max != run_max);
 #pragma unroll
-    for (int j = PER - 1; j >= 0; --j) {
-      const float e = E::get(ch, j);
-      const bool hit = isn ? (e != e) : (e == run_max);
-      if (hit) my_idx = (c_begin + run_chunk) * PER + j;
+    for (int u = U - 1; u >= 0; --u) {
+      const int c = (run_tile * U + u) * NT + gt;
+#pragma unroll
+      for (int j = PER - 1; j >= 0; --j) {
+        const float e = E::get(run_v[u], j);
+        const bool hit = (c < n) && (isn ? (e != e) : (e == run_max));
+        if (hit) my_idx = (c_begin + c) * PER + j;
+      }
     }
   }
-  block_argmax<NW, BAR>(my_val, my_idx, sc);
+  block_argmax<NW>(my_val, my_idx, sc, bar, lw);
 
   cg::cluster_group cluster = cg::this_cluster();
   if (S > 1) {
-    if (tid == 0) {
+    if (gt == 0) {
       sc.best_val = my_val;
       sc.best_idx = my_idx;
     }
@@ -243,28 +256,35 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
   float s = 0.f, sx = 0.f, sy = 0.f;
   if (MODE == MVGEO_SOFT_GLOBAL) {
     const float thr = M - p.skip_delta;  // NaN peak: every comparison is false, nothing accumulates
-    const uint4* cm4 = reinterpret_cast<const uint4*>(cmax);
-    const int groups = (n + PER - 1) / PER;
-    for (int g = tid; g < groups; g += NT) {
-      const uint4 cv = cm4[g];  // PER chunk maxima (carriers have the element type of the map)
-      if (E::chunk_max(cv) >= thr) {
+    const uint4* sm4 = reinterpret_cast<const uint4*>(smax);
+    const int groups = n_tiles * (NT / 8);
+    for (int g = gt; g < groups; g += NT) {
+      const uint4 cv = sm4[g];  // 8 slice maxima
+      if (CE::chunk_max(cv) >= thr) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          const int c = g * PER + j;
-          if (c < n && E::get(cv, j) >= thr) {
-            const uint4 ch = ld_stream(seg + c);
-            const int flat0 = (c_begin + c) * PER;
-            int y = flat0 / p.W, x = flat0 - y * p.W;
+        for (int j = 0; j < 8; ++j) {
+          if (CE::get(cv, j) >= thr) {
+            const int e = g * 8 + j;
+            const int t = e / NT, owner = e - t * NT;
 #pragma unroll
-            for (int e_ = 0; e_ < PER; ++e_) {
-              const float e = E::get(ch, e_);
-              const float w = ex2_approx((e - M) * p.beta_log2e);
-              s += w;
-              sx += w * (float)(x - px);
-              sy += w * (float)(y - py);
-              if (++x == p.W) {
-                x = 0;
-                ++y;
+            for (int u = 0; u < U; ++u) {
+              const int c = (t * U + u) * NT + owner;
+              if (c < n) {
+                const uint4 ch = ld_stream(seg + c);
+                const int flat0 = (c_begin + c) * PER;
+                int y = flat0 / p.W, x = flat0 - y * p.W;
+#pragma unroll
+                for (int e_ = 0; e_ < PER; ++e_) {
+                  const float el = E::get(ch, e_);
+                  const float w = ex2_approx((el - M) * p.beta_log2e);
+                  s += w;
+                  sx += w * (float)(x - px);
+                  sy += w * (float)(y - py);
+                  if (++x == p.W) {
+                    x = 0;
+                    ++y;
+                  }
+                }
               }
             }
           }
@@ -272,18 +292,18 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
       }
     }
   } else if (MODE == MVGEO_SOFT_WINDOW) {
-    if (rank == 0) window_accumulate<DT, NT>(p, mp, M, px, py, s, sx, sy);
+    if (rank == 0) window_accumulate<DT, NT>(p, mp, M, px, py, gt, s, sx, sy);
   }
   if (MODE != MVGEO_SOFT_NONE) {
-    block_sum3<NW, BAR>(s, sx, sy, sc);
+    block_sum3<NW>(s, sx, sy, sc, bar, lw);
     if (S > 1 && MODE == MVGEO_SOFT_GLOBAL) {
-      if (tid == 0) {
+      if (gt == 0) {
         sc.part[0] = s;
         sc.part[1] = sx;
         sc.part[2] = sy;
       }
       cluster.sync();
-      if (rank == 0 && tid == 0) {
+      if (rank == 0 && gt == 0) {
         s = sx = sy = 0.f;
         for (int r = 0; r < S; ++r) {  // fixed rank order: deterministic
           const BlockScratch* peer = cluster.map_shared_rank(&sc, r);
@@ -294,110 +314,61 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
       }
     }
   }
-  if (rank == 0 && tid == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
+  if (rank == 0 && gt == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
   if (S > 1) cluster.sync();  // peers' shared memory must outlive the remote reads above
 }
 
-// -inf padding of the chunk-maxima array up to a multiple of PER entries (see decode_epilogue)
-template <int DT>
-__device__ __forceinline__ void pad_cmax(typename Elem<DT>::carrier* cmax, int n) {
-  using E = Elem<DT>;
-  const int c = n + (int)threadIdx.x;
-  if ((int)threadIdx.x < E::kPerChunk && c < ((n + E::kPerChunk - 1) / E::kPerChunk) * E::kPerChunk)
-    cmax[c] = E::pack(__int_as_float(0xff800000));
-}
-
-// ---- streaming pass, variant A: register-staged ld.global.nc (kept for A/B measurements) ----
-template <int DT, int MODE>
-__global__ void __launch_bounds__(kDecThreads, 4) decode_vec_kernel(const DecodeParams p) {
-  using E = Elem<DT>;
-  using carrier = typename E::carrier;
-  __shared__ BlockScratch sc;
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  carrier* cmax = reinterpret_cast<carrier*>(dyn_smem);
-
-  const int S = p.splits;
-  const int64_t map = blockIdx.x / S;
-  const int rank = (int)(blockIdx.x - map * S);
-  const int tid = threadIdx.x;
-  const uint4* mp = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map;
-  const int c_begin = rank * p.seg_chunks;
-  const int n = max(min(c_begin + p.seg_chunks, p.chunks_per_map) - c_begin, 0);
-  const uint4* seg = mp + c_begin;
-
-  float run_max = __int_as_float(0xff800000);  // -inf
-  int run_chunk = tid < n ? tid : -1;
-  constexpr int kBatch = kDecThreads * kDecUnroll;
-  const int full = n / kBatch;
-  for (int it = 0; it < full; ++it) {
-    uint4 v[kDecUnroll];
-#pragma unroll
-    for (int u = 0; u < kDecUnroll; ++u) v[u] = ld_stream(seg + it * kBatch + u * kDecThreads + tid);
-#pragma unroll
-    for (int u = 0; u < kDecUnroll; ++u)
-      consume_chunk<DT, MODE>(v[u], it * kBatch + u * kDecThreads + tid, cmax, run_max, run_chunk);
-  }
-  for (int c = full * kBatch + tid; c < n; c += kDecThreads) {
-    const uint4 v = ld_stream(seg + c);
-    consume_chunk<DT, MODE>(v, c, cmax, run_max, run_chunk);
-  }
-  if (MODE == MVGEO_SOFT_GLOBAL) pad_cmax<DT>(cmax, n);
-  decode_epilogue<DT, MODE, kDecWarps, 0>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
-}
-
-// ---- streaming pass, variant B: TMA bulk copies into a shared-memory ring -------------------
-// One producer lane issues cp.async.bulk (SASS UBLKCP) tiles of 256*U chunks into a STAGES-deep
-// ring with full/empty mbarriers per stage; the 8 consumer warps read each tile with
-// conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by registers, and the
-// consumers carry no global address arithmetic.
-// PERSIST (maps that fit one CTA): the grid is (SMs x resident CTAs) and every CTA walks maps
-// blockIdx.x, +gridDim.x, ...; the producer keeps filling the ring with the NEXT map's tiles
-// while the consumers are in the latency-bound epilogue of the current one (they synchronise on
-// a consumer-only named barrier), so the epilogue no longer drains the memory pipeline.
-// !PERSIST (maps split over a thread-block cluster): one segment per CTA, whole CTA in the epilogue.
-template <int DT, int MODE, int U, int STAGES, bool PERSIST>
+// G independent consumer groups per CTA (8/G warps each, own ring, own mbarriers, own named
+// barrier, own map sequence): small maps use G > 1 so that one group's latency-bound epilogue
+// overlaps the other groups' streaming. Producer lane g of the 9th warp feeds group g.
+// PERSIST: grid = one resident wave, group (blockIdx.x, g) walks maps blockIdx.x*G + g, +gridDim.x*G, ...
+// !PERSIST (G == 1): one segment of a cluster-split map per CTA, producer warp joins the epilogue.
+template <int DT, int MODE, int U, int STAGES, int G, bool PERSIST>
 __global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const DecodeParams p) {
-  using E = Elem<DT>;
-  using carrier = typename E::carrier;
-  constexpr int kTile = kDecThreads * U;  // chunks per tile
-  __shared__ BlockScratch sc;
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  static_assert(PERSIST || G == 1, "cluster-split maps use one consumer group");
+  constexpr int NW = kDecWarps / G;  // consumer warps per group
+  constexpr int NT = NW * 32;
+  constexpr int kTile = NT * U;  // chunks per tile of one group
+  __shared__ BlockScratch sc[G];
+  __shared__ __align__(8) uint64_t full_bar[G][STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[G][STAGES];
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  uint4* ring = reinterpret_cast<uint4*>(dyn_smem);
-  carrier* cmax = reinterpret_cast<carrier*>(dyn_smem + (size_t)STAGES * kTile * 16);
 
   const int S = PERSIST ? 1 : p.splits;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t first = PERSIST ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / S);
-  const int64_t step = PERSIST ? (int64_t)gridDim.x : p.n_maps;  // !PERSIST: exactly one map
-  const int rank = PERSIST ? 0 : (int)(blockIdx.x - first * S);
+  const int rank = PERSIST ? 0 : (int)(blockIdx.x % S);
   const int c_begin = rank * p.seg_chunks;
   const int n = max(min(c_begin + p.seg_chunks, p.chunks_per_map) - c_begin, 0);
   const int n_tiles = (n + kTile - 1) / kTile;
+  const int64_t step = PERSIST ? (int64_t)gridDim.x * G : p.n_maps;  // !PERSIST: exactly one map
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kDecWarps);
-    }
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[g][s], 1);
+        mbar_init(&empty_bar[g][s], NW);
+      }
     mbar_fence_init();
   }
   __syncthreads();
 
   if (warp == kDecWarps) {
-    // ------------------------------- producer ---------------------------------------------
-    if (lane == 0) {
+    // ------------------------------- producers --------------------------------------------
+    if (lane < G) {
+      const int g = lane;
+      uint4* ring = reinterpret_cast<uint4*>(dyn_smem) + (size_t)g * STAGES * kTile;
+      const int64_t first = PERSIST ? (int64_t)blockIdx.x * G + g : (int64_t)(blockIdx.x / S);
       int s = 0, k = 0;  // slot, and how many times the ring has wrapped
       for (int64_t map = first; map < p.n_maps; map += step) {
         const uint4* seg = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map + c_begin;
         for (int t = 0; t < n_tiles; ++t) {
           // before re-using a slot for the k-th time, wait for the consumers' (k-1)-th release of it
-          if (k > 0) mbar_wait(&empty_bar[s], (uint32_t)((k - 1) & 1));
+          if (k > 0) mbar_wait(&empty_bar[g][s], (uint32_t)((k - 1) & 1));
           const uint32_t bytes = (uint32_t)min(kTile, n - t * kTile) * 16u;
-          mbar_arrive_expect_tx(&full_bar[s], bytes);
-          bulk_copy_g2s(ring + s * kTile, seg + (size_t)t * kTile, bytes, &full_bar[s]);
+          mbar_arrive_expect_tx(&full_bar[g][s], bytes);
+          bulk_copy_g2s(ring + s * kTile, seg + (size_t)t * kTile, bytes, &full_bar[g][s]);
           if (++s == STAGES) {
             s = 0;
             ++k;
@@ -409,35 +380,54 @@ __global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const Deco
   }
 
   // --------------------------------- consumers ---------------------------------------------
+  const bool consumer = warp < kDecWarps;
+  const int g = consumer ? warp / NW : 0;
+  const int gt = PERSIST ? tid - g * NT : tid;  // thread index inside the group
+  const uint4* ring = reinterpret_cast<const uint4*>(dyn_smem) + (size_t)g * STAGES * kTile;
+  uint16_t* smax = reinterpret_cast<uint16_t*>(dyn_smem + (size_t)G * STAGES * kTile * 16) + (size_t)g * n_tiles * NT;
+  const int64_t first = PERSIST ? (int64_t)blockIdx.x * G + g : (int64_t)(blockIdx.x / S);
   int s = 0;
   uint32_t ph = 0;
   for (int64_t map = first; map < p.n_maps; map += step) {
     const uint4* mp = reinterpret_cast<const uint4*>(p.maps) + map * (int64_t)p.chunks_per_map;
     float run_max = __int_as_float(0xff800000);  // -inf
-    int run_chunk = -1;
-    if (warp < kDecWarps) {
-      run_chunk = tid < n ? tid : -1;
-      if (MODE == MVGEO_SOFT_GLOBAL) pad_cmax<DT>(cmax, n);
+    int run_tile = -1;
+    uint4 run_v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) run_v[u] = Elem<DT>::neg_inf_chunk();  // an all -inf map resolves to index 0
+    if (consumer) {
+      run_tile = gt < n ? 0 : -1;
       for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&full_bar[g][s], ph);
         const uint4* tile = ring + s * kTile;
         const int base = t * kTile;
+        // vertical (packed) maximum over the thread's slice, then ONE horizontal step and ONE
+        // running-maximum update per tile. The slice maximum is canonicalised (+0.0f turns -0 into
+        // +0) so that the update test is a bit comparison of max.NaN results: equal values, -0/+0
+        // and NaN/NaN all keep the FIRST slice.
+        uint4 v[U];
         if (base + kTile <= n) {
-          uint4 v[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) v[u] = tile[u * kDecThreads + tid];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            consume_chunk<DT, MODE>(v[u], base + u * kDecThreads + tid, cmax, run_max, run_chunk);
+          for (int u = 0; u < U; ++u) v[u] = tile[u * NT + gt];
         } else {
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int c = base + u * kDecThreads + tid;
-            if (c < n) consume_chunk<DT, MODE>(tile[u * kDecThreads + tid], c, cmax, run_max, run_chunk);
-          }
+          for (int u = 0; u < U; ++u)
+            v[u] = (base + u * NT + gt < n) ? tile[u * NT + gt] : Elem<DT>::neg_inf_chunk();
         }
+        uint32_t vm = Elem<DT>::vmax(v[0]);
+#pragma unroll
+        for (int u = 1; u < U; ++u) vm = Elem<DT>::vmerge(vm, Elem<DT>::vmax(v[u]));
+        const float sm = Elem<DT>::vfinish(vm) + 0.0f;
+        if (MODE == MVGEO_SOFT_GLOBAL) smax[t * NT + gt] = to_carrier<DT>(sm);
+        const float nm = max_nan_f32(run_max, sm);
+        if (__float_as_uint(nm) != __float_as_uint(run_max)) {  // strictly better: remember the slice itself
+          run_tile = t;
+#pragma unroll
+          for (int u = 0; u < U; ++u) run_v[u] = v[u];
+        }
+        run_max = nm;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive(&empty_bar[g][s]);
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
@@ -445,9 +435,11 @@ __global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const Deco
       }
     }
     if (PERSIST)
-      decode_epilogue<DT, MODE, kDecWarps, 1>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
+      decode_epilogue<DT, MODE, NW, U>(p, sc[g], smax, mp, map, rank, c_begin, n, n_tiles, run_max, run_tile, run_v,
+                                       1 + g, gt);
     else
-      decode_epilogue<DT, MODE, kDecWarps + 1, 0>(p, sc, cmax, mp, map, rank, c_begin, n, run_max, run_chunk);
+      decode_epilogue<DT, MODE, kDecWarps + 1, U>(p, sc[0], smax, mp, map, rank, c_begin, n, n_tiles, run_max,
+                                                  run_tile, run_v, 0, gt);
   }
 }
 
@@ -473,7 +465,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
       my_idx = i;
     }
   }
-  block_argmax<kDecWarps, 0>(my_val, my_idx, sc);
+  block_argmax<kDecWarps>(my_val, my_idx, sc, 0, tid >> 5);
   const float M = my_val;
   const int best = my_idx;
   const int py = best / p.W, px = best - py * p.W;
@@ -491,9 +483,9 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
       }
     }
   } else if (MODE == MVGEO_SOFT_WINDOW) {
-    window_accumulate<DT, kDecThreads>(p, base, M, px, py, s, sx, sy);
+    window_accumulate<DT, kDecThreads>(p, base, M, px, py, tid, s, sx, sy);
   }
-  if (MODE != MVGEO_SOFT_NONE) block_sum3<kDecWarps, 0>(s, sx, sy, sc);
+  if (MODE != MVGEO_SOFT_NONE) block_sum3<kDecWarps>(s, sx, sy, sc, 0, tid >> 5);
   if (tid == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
 }
 
@@ -506,6 +498,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 #endif
 constexpr int kTmaU = MVGEO_TMA_U;
 constexpr int kTmaStages = MVGEO_TMA_STAGES;
+constexpr int kMaxTableBytes = 150 * 1024;  // slice-maxima table budget per CTA
 
 template <typename K>
 static int launch_clustered(K kern, const DecodeParams& p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
@@ -526,22 +519,9 @@ static int launch_clustered(K kern, const DecodeParams& p, unsigned grid, int th
   return MVGEO_OK;
 }
 
-template <int DT, int MODE>
-static int launch_decode(const DecodeParams& p, bool vec, size_t cmax_bytes, int variant, cudaStream_t st) {
-  if (!vec) {
-    decode_scalar_kernel<DT, MODE><<<(unsigned)p.n_maps, kDecThreads, 0, st>>>(p);
-    MVGEO_CHECK_LAUNCH();
-    return MVGEO_OK;
-  }
-  const unsigned one_per_segment = (unsigned)(p.n_maps * p.splits);
-  if (variant == 0)
-    return launch_clustered(decode_vec_kernel<DT, MODE>, p, one_per_segment, kDecThreads, cmax_bytes, st);
-  const size_t smem = (size_t)kTmaStages * kTmaU * kDecThreads * 16 + cmax_bytes;
-  if (p.splits > 1)
-    return launch_clustered(decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, false>, p, one_per_segment,
-                            kDecThreads + 32, smem, st);
-  // persistent: one resident wave of CTAs, each walking maps blockIdx.x, +gridDim.x, ...
-  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, true>;
+template <int DT, int MODE, int G>
+static int launch_persistent(const DecodeParams& p, size_t smem, cudaStream_t st) {
+  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G, true>;
   if (smem > 40 * 1024) MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0, per_sm = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
@@ -549,16 +529,34 @@ static int launch_decode(const DecodeParams& p, bool vec, size_t cmax_bytes, int
   MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32, smem));
   if (per_sm < 1) return MVGEO_EUNSUPPORTED;
   const int64_t resident = (int64_t)sms * per_sm;
-  const unsigned grid = (unsigned)(p.n_maps < resident ? p.n_maps : resident);
-  return launch_clustered(kern, p, grid, kDecThreads + 32, smem, st);
+  const int64_t wanted = (p.n_maps + G - 1) / G;
+  return launch_clustered(kern, p, (unsigned)(wanted < resident ? wanted : resident), kDecThreads + 32, smem, st);
+}
+
+template <int DT, int MODE>
+static int launch_decode(const DecodeParams& p, bool vec, int groups, size_t table_bytes, cudaStream_t st) {
+  if (!vec) {
+    decode_scalar_kernel<DT, MODE><<<(unsigned)p.n_maps, kDecThreads, 0, st>>>(p);
+    MVGEO_CHECK_LAUNCH();
+    return MVGEO_OK;
+  }
+  const size_t smem = (size_t)kTmaStages * kTmaU * kDecThreads * 16 + table_bytes;
+  if (p.splits > 1)
+    return launch_clustered(decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, 1, false>, p,
+                            (unsigned)(p.n_maps * p.splits), kDecThreads + 32, smem, st);
+  switch (groups) {
+    case 4: return launch_persistent<DT, MODE, 4>(p, smem, st);
+    case 2: return launch_persistent<DT, MODE, 2>(p, smem, st);
+    default: return launch_persistent<DT, MODE, 1>(p, smem, st);
+  }
 }
 
 template <int DT>
-static int dispatch_mode(const DecodeParams& p, int mode, bool vec, size_t smem, int variant, cudaStream_t st) {
+static int dispatch_mode(const DecodeParams& p, int mode, bool vec, int groups, size_t table_bytes, cudaStream_t st) {
   switch (mode) {
-    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, vec, 0, variant, st);
-    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, vec, smem, variant, st);
-    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, vec, 0, variant, st);
+    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, vec, groups, 0, st);
+    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, vec, groups, table_bytes, st);
+    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, vec, groups, 0, st);
   }
   return MVGEO_EINVAL;
 }
@@ -608,29 +606,37 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
   p.seg_chunks = 0;
   p.splits = 1;
   size_t smem = 0;
+  int groups = 1;
   if (vec) {
-    // The split count depends on the map size only (never on n_maps), so results are
-    // bit-identical however the frames are sharded across GPUs.
+    // Work decomposition is a function of the map size only (never of n_maps), so results are
+    // bit-identical however the frames are sharded across GPUs:
+    //   small maps  -> several consumer groups per CTA, one map stream each (epilogues overlap);
+    //   large maps  -> one group; split over a cluster only when the slice-maxima table
+    //                  (2 bytes per kTmaU chunks) cannot fit one CTA.
     const int64_t chunks = map_bytes / 16;
+    const char* eg = getenv("MVGEO_DECODE_GROUPS");  // kernel-development override
+    if (eg) groups = atoi(eg);
+    else groups = map_bytes <= 112 * 1024 ? 4 : 1;
+    if (groups != 1 && groups != 2 && groups != 4) return MVGEO_EINVAL;
+    const int64_t tile = (int64_t)(kDecThreads / groups) * kTmaU;
     int splits = 1;
-    if (map_bytes > 192 * 1024) splits = (int)min((int64_t)kMaxSplits, (map_bytes + 160 * 1024 - 1) / (160 * 1024));
+    while (splits < kMaxSplits && ((chunks + splits - 1) / splits + tile - 1) / tile * kDecThreads * 2 > kMaxTableBytes)
+      ++splits;
+    if (splits > 1) groups = 1;
     p.chunks_per_map = (int)chunks;
     p.seg_chunks = (int)((chunks + splits - 1) / splits);
     p.splits = splits;
     if (soft_mode == MVGEO_SOFT_GLOBAL) {
-      smem = (size_t)((p.seg_chunks + 7) / 8 * 8) * (dtype == MVGEO_F32 ? 4 : 2);  // padded for the 16-byte scan
-      if (smem > 150 * 1024) return MVGEO_EUNSUPPORTED;  // maps beyond ~6.4 MB (f32): use the window mode
+      const int64_t tile1 = (int64_t)(kDecThreads / groups) * kTmaU;
+      smem = (size_t)((p.seg_chunks + tile1 - 1) / tile1) * kDecThreads * 2;  // all groups' tables
+      if (smem > (size_t)kMaxTableBytes) return MVGEO_EUNSUPPORTED;  // maps beyond ~19 MB: use the window mode
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // A/B switch for kernel development only (MVGEO_DECODE_VARIANT=0 selects the register-staged
-  // ld.global variant); both variants produce bit-identical results.
-  const char* ev = getenv("MVGEO_DECODE_VARIANT");
-  const int variant = (ev && ev[0] == '0') ? 0 : 1;
   switch (dtype) {
-    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, smem, variant, st);
-    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, vec, smem, variant, st);
-    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, vec, smem, variant, st);
+    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, groups, smem, st);
+    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, vec, groups, smem, st);
+    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, vec, groups, smem, st);
   }
   return MVGEO_EINVAL;
 }

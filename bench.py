@@ -45,6 +45,22 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per decode launch from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_decode_raw_selected.csv)."""
+    import csv
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_decode_raw_selected.csv")) as f:
+            rows = list(csv.reader(f))
+        hdr, units, first = rows[0], rows[1], rows[2]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        return float(first[rd]) * scale[units[rd]] + float(first[wr]) * scale[units[wr]]
+    except Exception:
+        return None
+
+
 def _intrinsics():
     import mvgeo
 
@@ -267,7 +283,8 @@ def run_ours(args):
                        "l2": "inputs are 5.03 GB per step per GPU (>> 126 MB L2): no flush needed",
                        "result_gather": "one nccl all_gather_into_tensor per step (X_tri, kp_soft, score, X_fk)" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "decode_tma_kernel<bf16, global, persistent>", "peak_source": peak_src,
+                         "traffic": _profiled_traffic(), "algorithmic_bytes": frame_bytes * B,
+                         "kernel": "decode_tma_kernel<bf16, global, persistent>", "peak_source": peak_src,
                          "decode_ms": dec_mean, "decode_share_of_step": dec_mean * args.steps / elapsed_ms,
                          "frac_of_nominal_8TBps": achieved / 8000.0, "bytes_per_frame": frame_bytes},
             "e2e": {"value": (B * world * e2e_steps / e2e_s) if e2e_steps else None, "unit": "frames/s", "h2d_bytes_per_step": h2d,

@@ -519,3 +519,40 @@ def test_full_size_round_trip_c2(mv):
     out2 = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size, soft="global", beta=100.0, min_score=0.5)
     for name in ("idx", "kp_soft", "X_tri", "loss"):
         assert torch.equal(out[name], out2[name])
+
+
+# ================================================ config 4: training step through both loss kernels
+def test_training_step_losses_have_correct_gradients(mv):
+    """Heat-map MSE + reprojection loss inside an autograd graph (the C4 training step): gradients
+    w.r.t. network outputs equal those of the float64 restatements, and SGD on them lowers the loss."""
+    rng = np.random.default_rng(21)
+    chain = mv.Chain.builtin("fr5")
+    V, B, K, J, HM = 3, 4, chain.n_points, chain.n_joints, 32
+    rig = mv.CameraRig.synthetic_ring_for("fr5", V, distortion=True)
+    Rv = np.stack([np.asarray(mv.view_rotation("fr5", v)) for v in ("top", "left", "right")]).astype(np.float32)
+    gt_q = torch.from_numpy(rng.uniform(-100, 100, (B, J)).astype(np.float32)).to(DEV)
+    gt_uv = mv.project_points(mv.forward_kinematics(chain, gt_q, Rv), rig)
+    Hi, Wi = rig.image_size
+    gt_kp = (gt_uv * torch.tensor([HM / Wi, HM / Hi], device=DEV)).reshape(B * V, K, 2)
+    q = (gt_q + torch.from_numpy(rng.normal(0, 5, (B, J)).astype(np.float32)).to(DEV)).requires_grad_(True)
+    maps = torch.from_numpy(rng.normal(0, 0.2, (B * V, K, HM, HM)).astype(np.float32)).to(DEV).requires_grad_(True)
+    opt = torch.optim.SGD([q, maps], lr=1.0)
+    losses = []
+    for it in range(5):
+        l_kpt = mv.heatmap_mse_loss(maps, gt_kp, sigma=2.0, weight=100.0)
+        l_fk, _, _, _ = mv.fk_reproj_loss(chain, q, rig, gt_uv, Rv, lam=1e-3)
+        loss = l_kpt + l_fk
+        opt.zero_grad()
+        loss.backward()
+        if it == 0:
+            lo, go = O.heatmap_mse(maps.detach().cpu().numpy().reshape(-1, HM, HM), gt_kp.cpu().numpy().reshape(-1, 2), 2.0, 100.0)
+            np.testing.assert_allclose(maps.grad.cpu().numpy().reshape(-1, HM, HM), go, rtol=1e-5, atol=1e-6 * np.abs(go).max())
+            cams = [dict(R=rig.R[v].astype(np.float32), t=rig.t[v].astype(np.float32), K=rig.K[v].astype(np.float32),
+                         dist=rig.dist[v].astype(np.float32)) for v in range(V)]
+            qt = torch.tensor(q.detach().cpu().numpy().astype(np.float64), requires_grad=True)
+            lf, _, _ = O.fk_reproj_loss_torch(O.chain_spec("fr5"), qt, Rv, cams, gt_uv.cpu().numpy(), None, 1e-3)
+            (gq,) = torch.autograd.grad(lf, qt)
+            assert np.abs(q.grad.cpu().numpy() - gq.numpy()).max() <= 1e-4 * np.abs(gq.numpy()).max()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]

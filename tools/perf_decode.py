@@ -17,15 +17,29 @@ for b0 in range(0, B, 64):
     sl = maps[b0:b0 + 64]
     sl.add_(torch.randn(sl.shape, generator=g, device=dev, dtype=torch.float32).mul_(0.01).to(dtype))
 nbytes = maps.numel() * maps.element_size()
+import ctypes as C
+lib = mvgeo._lib.load()
+n_maps = B * V * K
+idx = torch.empty((n_maps,), dtype=torch.int32, device=dev)
+peak, score = torch.empty((n_maps,), device=dev), torch.empty((n_maps,), device=dev)
+kph, kps = torch.empty((n_maps, 2), device=dev), torch.empty((n_maps, 2), device=dev)
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype]
+MODE = {"none": 0, "global": 1, "window": 2}[mode]
+st = torch.cuda.current_stream().cuda_stream
+def run():
+    rc = lib.mvgeo_decode(maps.data_ptr(), DT, n_maps, H, W, 1920 / W, 1200 / H, MODE, 100.0, 3, 0, 1, 1, 0, idx.data_ptr(),
+                          peak.data_ptr(), score.data_ptr(), kph.data_ptr(), kps.data_ptr(), st)
+    assert rc == 0, rc
 for _ in range(3):
-    r = mvgeo.decode_heatmaps(maps, (1200, 1920), soft=None if mode == "none" else mode, beta=100.0)
+    run()
 torch.cuda.synchronize()
 ts = []
-for _ in range(20):
+for _ in range(30):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); r = mvgeo.decode_heatmaps(maps, (1200, 1920), soft=None if mode == "none" else mode, beta=100.0); e1.record()
+    e0.record(); run(); e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 med, best = statistics.median(ts), min(ts)
-chk = int(r.idx.sum()), float(r.kp_soft.double().sum())
-print(f"{os.environ.get('MVGEO_LIB','default'):40s} var={os.environ.get('MVGEO_DECODE_VARIANT','1')} {B}x{V}x{K}x{H}x{W} {a[5] if len(a)>5 else 'bf16'} {mode:6s} "
+chk = int(idx.sum()), float(kps.double().sum())
+tag = os.path.basename(os.environ.get('MVGEO_LIB', 'default')) + " g=" + os.environ.get('MVGEO_DECODE_GROUPS', '-')
+print(f"{tag:28s} {B}x{V}x{K}x{H}x{W} {a[5] if len(a)>5 else 'bf16'} {mode:6s} "
       f"median {med*1e3:8.1f} us  {nbytes/med/1e6:8.1f} GB/s   best {nbytes/best/1e6:8.1f} GB/s  chk={chk}")

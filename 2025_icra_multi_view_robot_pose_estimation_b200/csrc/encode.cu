@@ -65,133 +65,200 @@ __device__ __forceinline__ bool gaussian_tables(const float* __restrict__ kp, in
   return ok;
 }
 
-template <int DT, bool VEC>
+// Gaussian value of PER consecutive pixels of one row starting at x (x % 4 == 0): two/one 16-byte
+// table reads instead of PER scalar ones.
+template <int PER>
+__device__ __forceinline__ void row_values(const float* ex, int x, float vy, float thr, float* v) {
+#pragma unroll
+  for (int q = 0; q < PER / 4; ++q) {
+    const float4 e = *reinterpret_cast<const float4*>(ex + x + 4 * q);
+    const float g0 = e.x * vy, g1 = e.y * vy, g2 = e.z * vy, g3 = e.w * vy;
+    v[4 * q + 0] = g0 < thr ? 0.f : g0;
+    v[4 * q + 1] = g1 < thr ? 0.f : g1;
+    v[4 * q + 2] = g2 < thr ? 0.f : g2;
+    v[4 * q + 3] = g3 < thr ? 0.f : g3;
+  }
+}
+
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// VEC: 16-byte stores; ROW additionally W % PER == 0, so a chunk never straddles two rows.
+template <int DT, bool VEC, bool ROW>
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const float* __restrict__ kp, int64_t n_maps, int H,
                                                              int W, float inv_2s2_log2e, void* __restrict__ maps) {
   using E = Elem<DT>;
-  extern __shared__ float tab[];
+  extern __shared__ __align__(16) float tab[];
   float* ex = tab;
-  float* ey = tab + W;
-  const int64_t map = blockIdx.x;
-  float thr;
-  gaussian_tables(kp, map, H, W, inv_2s2_log2e, ex, ey, thr);
+  float* ey = tab + ((W + 3) & ~3);
   const int n = H * W;
-  if (VEC) {
-    constexpr int PER = E::kPerChunk;
-    uint4* out = reinterpret_cast<uint4*>(maps) + map * (int64_t)(n / PER);
-    for (int c = threadIdx.x; c < n / PER; c += kEncThreads) {
-      const int flat0 = c * PER;
-      int y = flat0 / W, x = flat0 - y * W;
-      float vy = ey[y];
-      float v[PER];
+  for (int64_t map = blockIdx.x; map < n_maps; map += gridDim.x) {
+    float thr;
+    gaussian_tables(kp, map, H, W, inv_2s2_log2e, ex, ey, thr);
+    if (VEC) {
+      constexpr int PER = E::kPerChunk;
+      uint4* out = reinterpret_cast<uint4*>(maps) + map * (int64_t)(n / PER);
+      const int cpr = W / PER;  // chunks per row (ROW only)
+      for (int c = threadIdx.x; c < n / PER; c += kEncThreads) {
+        float v[PER];
+        if (ROW) {
+          const int y = c / cpr, x = (c - y * cpr) * PER;
+          row_values<PER>(ex, x, ey[y], thr, v);
+        } else {
+          const int flat0 = c * PER;
+          int y = flat0 / W, x = flat0 - y * W;
+          float vy = ey[y];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const float g = ex[x] * vy;
-        v[j] = g < thr ? 0.f : g;
-        if (++x == W) {
-          x = 0;
-          ++y;
-          vy = y < H ? ey[y] : 0.f;
+          for (int j = 0; j < PER; ++j) {
+            const float g = ex[x] * vy;
+            v[j] = g < thr ? 0.f : g;
+            if (++x == W) {
+              x = 0;
+              ++y;
+              vy = y < H ? ey[y] : 0.f;
+            }
+          }
         }
+        st_stream(out + c, pack_chunk<DT>(v));
       }
-      out[c] = pack_chunk<DT>(v);
+    } else {
+      char* out = reinterpret_cast<char*>(maps) + map * (int64_t)n * E::kBytes;
+      for (int i = threadIdx.x; i < n; i += kEncThreads) {
+        const int y = i / W, x = i - y * W;
+        const float g = ex[x] * ey[y];
+        E::store(out, i, g < thr ? 0.f : g);
+      }
     }
-  } else {
-    char* out = reinterpret_cast<char*>(maps) + map * (int64_t)n * E::kBytes;
-    for (int i = threadIdx.x; i < n; i += kEncThreads) {
-      const int y = i / W, x = i - y * W;
-      const float g = ex[x] * ey[y];
-      E::store(out, i, g < thr ? 0.f : g);
-    }
+    __syncthreads();  // tables are rebuilt for the next map
   }
 }
 
 // pred - gaussian(kp): per-map sum of squares (fixed-order reduction) and optional gradient.
-template <int DT, bool VEC, bool GRAD>
-__global__ void __launch_bounds__(kEncThreads)
+// Four 16-byte loads in flight per thread (the loads of a batch are issued before any is used).
+template <int DT, bool VEC, bool ROW, bool GRAD>
+__global__ void __launch_bounds__(kEncThreads, 4)
     mse_kernel(const void* __restrict__ pred, const float* __restrict__ kp, int64_t n_maps, int H, int W,
                float inv_2s2_log2e, float grad_scale, float* __restrict__ partial, void* __restrict__ grad) {
   using E = Elem<DT>;
-  extern __shared__ float tab[];
+  extern __shared__ __align__(16) float tab[];
   __shared__ float red[kEncWarps];
   float* ex = tab;
-  float* ey = tab + W;
-  const int64_t map = blockIdx.x;
-  float thr;
-  gaussian_tables(kp, map, H, W, inv_2s2_log2e, ex, ey, thr);
+  float* ey = tab + ((W + 3) & ~3);
   const int n = H * W;
-  float acc = 0.f;
-  if (VEC) {
-    constexpr int PER = E::kPerChunk;
-    const uint4* in = reinterpret_cast<const uint4*>(pred) + map * (int64_t)(n / PER);
-    uint4* gout = GRAD ? reinterpret_cast<uint4*>(grad) + map * (int64_t)(n / PER) : nullptr;
-    for (int c = threadIdx.x; c < n / PER; c += kEncThreads) {
-      const uint4 ch = ld_stream(in + c);
-      const int flat0 = c * PER;
-      int y = flat0 / W, x = flat0 - y * W;
-      float vy = ey[y];
-      float gv[PER];
+  for (int64_t map = blockIdx.x; map < n_maps; map += gridDim.x) {
+    float thr;
+    gaussian_tables(kp, map, H, W, inv_2s2_log2e, ex, ey, thr);
+    float acc = 0.f;
+    if (VEC) {
+      constexpr int PER = E::kPerChunk;
+      constexpr int UN = 4;
+      const int nc = n / PER, cpr = ROW ? W / PER : 1;
+      const uint4* in = reinterpret_cast<const uint4*>(pred) + map * (int64_t)nc;
+      uint4* gout = GRAD ? reinterpret_cast<uint4*>(grad) + map * (int64_t)nc : nullptr;
+      for (int c0 = threadIdx.x; c0 < nc; c0 += kEncThreads * UN) {
+        uint4 ch[UN];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        float g = ex[x] * vy;
-        g = g < thr ? 0.f : g;
-        const float d = E::get(ch, j) - g;
-        acc += d * d;
-        gv[j] = d * grad_scale;
-        if (++x == W) {
-          x = 0;
-          ++y;
-          vy = y < H ? ey[y] : 0.f;
+        for (int u = 0; u < UN; ++u) {
+          const int c = c0 + u * kEncThreads;
+          ch[u] = c < nc ? ld_stream(in + c) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int c = c0 + u * kEncThreads;
+          if (c < nc) {
+            float g[PER], gv[PER];
+            if (ROW) {
+              const int y = c / cpr, x = (c - y * cpr) * PER;
+              row_values<PER>(ex, x, ey[y], thr, g);
+            } else {
+              const int flat0 = c * PER;
+              int y = flat0 / W, x = flat0 - y * W;
+              float vy = ey[y];
+#pragma unroll
+              for (int j = 0; j < PER; ++j) {
+                const float t = ex[x] * vy;
+                g[j] = t < thr ? 0.f : t;
+                if (++x == W) {
+                  x = 0;
+                  ++y;
+                  vy = y < H ? ey[y] : 0.f;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+              const float d = E::get(ch[u], j) - g[j];
+              acc += d * d;
+              gv[j] = d * grad_scale;
+            }
+            if (GRAD) st_stream(gout + c, pack_chunk<DT>(gv));
+          }
         }
       }
-      if (GRAD) gout[c] = pack_chunk<DT>(gv);
+    } else {
+      const char* in = reinterpret_cast<const char*>(pred) + map * (int64_t)n * E::kBytes;
+      char* gout = GRAD ? reinterpret_cast<char*>(grad) + map * (int64_t)n * E::kBytes : nullptr;
+      for (int i = threadIdx.x; i < n; i += kEncThreads) {
+        const int y = i / W, x = i - y * W;
+        float g = ex[x] * ey[y];
+        g = g < thr ? 0.f : g;
+        const float d = E::load(in, i) - g;
+        acc += d * d;
+        if (GRAD) E::store(gout, i, d * grad_scale);
+      }
     }
-  } else {
-    const char* in = reinterpret_cast<const char*>(pred) + map * (int64_t)n * E::kBytes;
-    char* gout = GRAD ? reinterpret_cast<char*>(grad) + map * (int64_t)n * E::kBytes : nullptr;
-    for (int i = threadIdx.x; i < n; i += kEncThreads) {
-      const int y = i / W, x = i - y * W;
-      float g = ex[x] * ey[y];
-      g = g < thr ? 0.f : g;
-      const float d = E::load(in, i) - g;
-      acc += d * d;
-      if (GRAD) E::store(gout, i, d * grad_scale);
-    }
-  }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < kEncWarps; ++w) t += red[w];
-    partial[map] = t;
+      for (int w = 0; w < kEncWarps; ++w) t += red[w];
+      partial[map] = t;
+    }
+    __syncthreads();  // red[] and the tables are reused for the next map
   }
 }
 
 __global__ void scale_kernel(float* x, float s) { x[0] *= s; }
 
+// Grid: enough CTAs for ~8 per SM; CTAs walk maps blockIdx.x, +gridDim.x (tables rebuilt per map).
+static unsigned maps_grid(int64_t n_maps) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t cap = (int64_t)sms * 8;
+  return (unsigned)(n_maps < cap ? n_maps : cap);
+}
+
 template <int DT>
 static int launch_encode(const float* kp, int64_t n_maps, int H, int W, float k, void* maps, bool vec, cudaStream_t st) {
-  const size_t smem = (size_t)(H + W) * sizeof(float);
-  if (vec) encode_kernel<DT, true><<<(unsigned)n_maps, kEncThreads, smem, st>>>(kp, n_maps, H, W, k, maps);
-  else encode_kernel<DT, false><<<(unsigned)n_maps, kEncThreads, smem, st>>>(kp, n_maps, H, W, k, maps);
+  const size_t smem = (size_t)(((W + 3) & ~3) + H) * sizeof(float);
+  const unsigned g = maps_grid(n_maps);
+  const bool row = vec && (W % Elem<DT>::kPerChunk == 0);
+  if (row) encode_kernel<DT, true, true><<<g, kEncThreads, smem, st>>>(kp, n_maps, H, W, k, maps);
+  else if (vec) encode_kernel<DT, true, false><<<g, kEncThreads, smem, st>>>(kp, n_maps, H, W, k, maps);
+  else encode_kernel<DT, false, false><<<g, kEncThreads, smem, st>>>(kp, n_maps, H, W, k, maps);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
+}
+
+template <int DT, bool VEC, bool ROW>
+static void launch_mse2(const void* pred, const float* kp, int64_t n_maps, int H, int W, float k, float gs,
+                        float* partial, void* grad, unsigned g, size_t smem, cudaStream_t st) {
+  if (grad) mse_kernel<DT, VEC, ROW, true><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
+  else mse_kernel<DT, VEC, ROW, false><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
 }
 
 template <int DT>
 static int launch_mse(const void* pred, const float* kp, int64_t n_maps, int H, int W, float k, float gs,
                       float* partial, void* grad, bool vec, cudaStream_t st) {
-  const size_t smem = (size_t)(H + W) * sizeof(float);
-  const unsigned g = (unsigned)n_maps;
-  if (vec) {
-    if (grad) mse_kernel<DT, true, true><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
-    else mse_kernel<DT, true, false><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
-  } else {
-    if (grad) mse_kernel<DT, false, true><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
-    else mse_kernel<DT, false, false><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
-  }
+  const size_t smem = (size_t)(((W + 3) & ~3) + H) * sizeof(float);
+  const unsigned g = maps_grid(n_maps);
+  const bool row = vec && (W % Elem<DT>::kPerChunk == 0);
+  if (row) launch_mse2<DT, true, true>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
+  else if (vec) launch_mse2<DT, true, false>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
+  else launch_mse2<DT, false, false>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }

@@ -243,6 +243,45 @@ def fk_reproj_loss(chain: Chain, q: torch.Tensor, cams, gt_uv: torch.Tensor, R_v
     return _FKReprojLoss.apply(q, chain, cams_t, gt_uv, Rv, w, lam)
 
 
+# ------------------------------------------------------------------- camera-pose refinement
+def pnp_refine(X: torch.Tensor, kp: torch.Tensor, cams, w: Optional[torch.Tensor] = None, *, min_weight: float = 0.0,
+               max_iters: int = 20):
+    """Batched camera-pose refinement (Levenberg-Marquardt on the reprojection error) per
+    (frame, view), started from the prior pose held in `cams` — the batched stand-in for
+    estimate_camera_pose's cv2.solvePnPRansac + fallback-to-prior (model/Fr5_model_train.ipynb:4707-4753).
+    X (B,K,3) or (B,V,K,3) object points; kp (B,V,K,2) image points; w (B,V,K) scores or None.
+    Returns rvec (B,V,3), tvec (B,V,3), rms (B,V) px, status (B,V) int32
+    (bit 0 solved with >= 4 points, bit 1 converged, bit 2 plausible 0.5 m < |t| < 5 m)."""
+    lib = _lib.load()
+    X = _need_cuda(X, "X", torch.float32)
+    kp = _need_cuda(kp, "kp", torch.float32)
+    dev = X.device
+    cams_t = cameras_to_device(cams, dev)
+    V = int(cams_t.shape[0])
+    if kp.dim() != 4 or kp.shape[1] != V or kp.shape[-1] != 2:
+        raise ValueError("kp must be (B, V, K, 2) with V matching the rig")
+    B, _, K, _ = kp.shape
+    if X.dim() == 3 and tuple(X.shape) == (B, K, 3):
+        per_view = 0
+    elif X.dim() == 4 and tuple(X.shape) == (B, V, K, 3):
+        per_view = 1
+    else:
+        raise ValueError("X must be (B,K,3) or (B,V,K,3)")
+    if w is not None:
+        w = _need_cuda(w, "w", torch.float32)
+        if tuple(w.shape) != (B, V, K):
+            raise ValueError("w must be (B, V, K)")
+    rvec = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
+    tvec = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
+    rms = torch.empty((B, V), dtype=torch.float32, device=dev)
+    status = torch.empty((B, V), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvgeo_pnp_refine(X.data_ptr(), per_view, kp.data_ptr(), _ptr(w), cams_t.data_ptr(), B, V, K,
+                                        float(min_weight), int(max_iters), rvec.data_ptr(), tvec.data_ptr(),
+                                        rms.data_ptr(), status.data_ptr(), _stream(dev)), "mvgeo_pnp_refine")
+    return rvec, tvec, rms, status
+
+
 # --------------------------------------------------------------- GT encoder and heat-map MSE
 def encode_gaussian(kp: torch.Tensor, heatmap_size, sigma: float, dtype=torch.float32) -> torch.Tensor:
     """Batched create_gt_heatmap (model/MvRoPose_FR3.py:65-73): kp (..., 2) in MAP pixels ->

@@ -59,7 +59,7 @@ class PackedResults:
         full = pr.all_gather()          # {"X_tri": (world, B, K, 3), ...}: views, no copy
     Requires the same frame count on every rank (weak-scaling batches)."""
 
-    def __init__(self, spec: Dict[str, tuple], device):
+    def __init__(self, spec: Dict[str, tuple], device, storage: torch.Tensor = None):
         self._spec, self._views, off = {}, {}, 0
         for name, (shape, dtype) in spec.items():
             if torch.empty((), dtype=dtype).element_size() != 4:
@@ -69,10 +69,24 @@ class PackedResults:
                 n *= int(d)
             self._spec[name] = (off, n, tuple(shape), dtype)
             off += n
-        self.flat = torch.empty((off,), dtype=torch.float32, device=device)
+        if storage is None:
+            storage = torch.empty((off,), dtype=torch.float32, device=device)
+        elif storage.dtype != torch.float32 or storage.numel() != off or not storage.is_contiguous():
+            raise ValueError(f"storage must be a contiguous float32 tensor of {off} elements")
+        self.flat = storage
         for name, (o, n, shape, dtype) in self._spec.items():
             self._views[name] = self.flat[o:o + n].view(dtype).view(shape)
         self._gathered = None
+
+    @staticmethod
+    def numel_of(spec: Dict[str, tuple]) -> int:
+        total = 0
+        for shape, _ in spec.values():
+            n = 1
+            for d in shape:
+                n *= int(d)
+            total += n
+        return total
 
     def __getitem__(self, name: str) -> torch.Tensor:
         return self._views[name]
@@ -80,13 +94,45 @@ class PackedResults:
     def keys(self):
         return self._views.keys()
 
-    def all_gather(self, group=None) -> Dict[str, torch.Tensor]:
+    def all_gather(self, group=None, async_op: bool = False):
+        """One collective for every result array. With async_op=True returns (views, work): the
+        gather runs on the communicator's own stream, overlapping whatever the caller launches
+        next; call work.wait() before reading the views or overwriting this buffer again."""
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return {k: v.unsqueeze(0) for k, v in self._views.items()}
+            views = {k: v.unsqueeze(0) for k, v in self._views.items()}
+            return (views, None) if async_op else views
         ws = dist.get_world_size(group)
         if self._gathered is None or self._gathered.numel() != ws * self.flat.numel():
             self._gathered = self.flat.new_empty((ws * self.flat.numel(),))  # concatenated form (gloo and nccl)
-        dist.all_gather_into_tensor(self._gathered, self.flat, group=group)
+        work = dist.all_gather_into_tensor(self._gathered, self.flat, group=group, async_op=async_op)
         g2 = self._gathered.view(ws, self.flat.numel())
-        return {name: g2[:, o:o + n].view(dtype).view((ws,) + shape)
-                for name, (o, n, shape, dtype) in self._spec.items()}
+        views = {name: g2[:, o:o + n].view(dtype).view((ws,) + shape)
+                 for name, (o, n, shape, dtype) in self._spec.items()}
+        return (views, work) if async_op else views
+
+
+class ResultRing:
+    """`slots` PackedResults laid out in ONE device buffer: batch k of a job writes its results
+    into slot k, and the whole job's results are exchanged with a single final
+    all_gather_into_tensor (the only collective of the path; nothing is exchanged per batch)."""
+
+    def __init__(self, spec: Dict[str, tuple], slots: int, device):
+        self.spec, self.slots = spec, int(slots)
+        self.record = PackedResults.numel_of(spec)
+        self.flat = torch.empty((self.slots * self.record,), dtype=torch.float32, device=device)
+        self.slot = [PackedResults(spec, device, self.flat[i * self.record:(i + 1) * self.record])
+                     for i in range(self.slots)]
+        self._gathered = None
+
+    def final_gather(self, used_slots: int = None, group=None) -> torch.Tensor:
+        """Gather slots [0, used_slots) of every rank: returns (world, used_slots, record) float32."""
+        n = self.slots if used_slots is None else int(used_slots)
+        src = self.flat[: n * self.record]
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return src.view(1, n, self.record)
+        ws = dist.get_world_size(group)
+        if self._gathered is None or self._gathered.numel() < ws * src.numel():
+            self._gathered = self.flat.new_empty((ws * self.slots * self.record,))
+        dst = self._gathered[: ws * src.numel()]
+        dist.all_gather_into_tensor(dst, src, group=group)
+        return dst.view(ws, n, self.record)

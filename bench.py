@@ -183,12 +183,15 @@ def run_ours(args):
     K = chain.n_points
     cams = ops.cameras_to_device(rig, dev)
     Rvt = torch.from_numpy(Rv).to(dev)
-    out = mvgeo.alloc_outputs(B, V, K, dev)
-    # the per-frame results that leave the GPU live back to back in one buffer: one collective
-    packed = mvgeo.sharding.PackedResults({"X_tri": ((B, K, 3), torch.float32), "kp_soft": ((B, V, K, 2), torch.float32),
-                                           "score": ((B, V, K), torch.float32), "X_fk": ((B, V, K, 3), torch.float32)}, dev)
-    for name in packed.keys():
-        out[name] = packed[name]
+    # Every batch of the job writes its per-frame results (everything that leaves the GPU) into its own
+    # slot of one device ring; the job's ONLY collective is the final gather of that ring.
+    spec = {"X_tri": ((B, K, 3), torch.float32), "kp_soft": ((B, V, K, 2), torch.float32),
+            "score": ((B, V, K), torch.float32), "X_fk": ((B, V, K, 3), torch.float32)}
+    n_slots = min(max(args.steps, 1), 128)
+    ring = mvgeo.sharding.ResultRing(spec, n_slots, dev)
+    scratch = mvgeo.alloc_outputs(B, V, K, dev)  # outputs that stay on the GPU (idx, peak, residuals, loss ...)
+    counter = [0]
+    out = dict(scratch)
     Hi, Wi = rig.image_size
     sx, sy = Wi / W, Hi / H
     n_maps = B * V * K
@@ -198,6 +201,13 @@ def run_ours(args):
     def step():
         """decode -> triangulate -> FK + reprojection consistency through the C ABI (the same three
         launches mvgeo_pipeline makes), with CUDA events around the decode kernel."""
+        j = counter[0] % n_slots
+        if world > 1 and counter[0] > 0 and j == 0:
+            ring.final_gather()  # ring full (more than 128 batches in the job): flush before re-use
+        counter[0] += 1
+        out = dict(scratch)
+        for name in spec:
+            out[name] = ring.slot[j][name]
         s = st.cuda_stream
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -212,8 +222,6 @@ def run_ours(args):
                                       out["kp_soft"].data_ptr(), None, 1.0, out["X_fk"].data_ptr(), out["uv_fk"].data_ptr(),
                                       out["frame_loss"].data_ptr(), out["loss"].data_ptr(), s)
         assert rc == 0, rc
-        if world > 1:  # the path's only communication: final result gather, < 1 KB per frame
-            packed.all_gather()
         return e0, e1
 
     def fence():
@@ -222,8 +230,16 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def drain():
+        """The path's only communication: one final gather of the job's results, < 1 KB per frame."""
+        if world > 1:
+            used = counter[0] % n_slots or min(counter[0], n_slots)
+            ring.final_gather(used)
+        counter[0] = 0
+
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     fence()
     sampler = ClockSampler(local)
     sampler.start()
@@ -231,11 +247,15 @@ def run_ours(args):
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record(st)
     dec_events = [step() for _ in range(args.steps)]
+    drain()  # the final result gather is inside the timed region
     t_end.record(st)
     fence()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     dec_ms = [a.elapsed_time(b) for a, b in dec_events]
+    out = dict(scratch)
+    for name in spec:
+        out[name] = ring.slot[(args.steps - 1) % n_slots][name]
     loss = float(out["loss"])
     assert np.isfinite(loss)
     frac_all_views = float((out["tri_views"] == V).float().mean())
@@ -281,7 +301,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "robot": ROBOT, "views": V, "keypoints": K, "frames_per_gpu_per_step": B,
                        "map": [H, W], "map_dtype": "bf16", "soft_argmax": f"global beta={BETA}",
                        "l2": "inputs are 5.03 GB per step per GPU (>> 126 MB L2): no flush needed",
-                       "result_gather": "one nccl all_gather_into_tensor per step (X_tri, kp_soft, score, X_fk)" if world > 1 else "none (1 GPU)"},
+                       "result_gather": "results of every batch (X_tri, kp_soft, score, X_fk) kept in a device ring; ONE final nccl all_gather_into_tensor per job, inside the timed region" if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _profiled_traffic(), "algorithmic_bytes": frame_bytes * B,
                          "kernel": "decode_tma_kernel<bf16, global, persistent>", "peak_source": peak_src,

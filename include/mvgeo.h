@@ -194,6 +194,23 @@ int mvgeo_fk_reproj_bwd(const mvgeo_chain* chain, const float* q, int64_t B,
                         const float* gt_uv, const float* w, float lambda,
                         const float* dloss, float* dq, void* stream);
 
+/* -------------------------------------------------- camera-pose refinement (PnP)
+ * The step after the hot path in the reference: estimate_camera_pose
+ * (model/Fr5_model_train.ipynb:4707-4753): FK points + decoded key-points with score >= threshold
+ * (at least 4) -> cv2.solvePnPRansac -> plausibility gate 0.5 m < |t| < 5 m
+ * (model/Franka_research3_model_train.ipynb:3696-3701) -> ArUco prior on failure (:4978-4993).
+ * Levenberg-Marquardt on the reprojection error per (frame, view), started from the prior pose
+ * held in cams[v].R / cams[v].t (so a refused or failed solve returns the prior).
+ *   X       [B, Vx, K, 3] f32 object points, Vx = V when x_per_view != 0 else 1
+ *   kp      [B, V, K, 2]  f32 image points;  w [B, V, K] f32 (nullable)
+ *   rvec    [B, V, 3] f32 (cv2 Rodrigues vector), tvec [B, V, 3] f32
+ *   rms     [B, V] f32 RMS reprojection error over the points used (NaN if < 4)     (nullable)
+ *   status  [B, V] i32 bit 0: >= 4 valid points (solved), bit 1: converged, bit 2: plausible |t|  (nullable)
+ */
+int mvgeo_pnp_refine(const float* X, int x_per_view, const float* kp, const float* w,
+                     const mvgeo_camera* cams, int64_t B, int V, int K, float min_weight, int max_iters,
+                     float* rvec, float* tvec, float* rms, int32_t* status, void* stream);
+
 /* -------------------------------------------------- GT belief-map encoder
  * Replaces create_gt_heatmap (model/MvRoPose_FR3.py:65-73, model/DREAM_Train.py:60-69):
  * exp(-((x-cx)^2+(y-cy)^2)/(2 sigma^2)), values below eps(double)*max set to 0.

@@ -506,3 +506,84 @@ def heatmap_mse(pred, kp, sigma: float, weight: float = 1.0):
     loss = weight * np.mean(diff * diff)
     grad = weight * 2.0 * diff / diff.size
     return loss, grad
+
+
+# --------------------------------------------------------------------------------------
+# Camera-pose refinement ("next" row 3; specification, cross-checked against cv2.solvePnP)
+# --------------------------------------------------------------------------------------
+def rvec_from_matrix(R) -> np.ndarray:
+    """cv2.Rodrigues(R)[0]: rotation matrix -> rotation vector (float64)."""
+    R = np.asarray(R, dtype=np.float64)
+    c = min(1.0, max(-1.0, 0.5 * (np.trace(R) - 1.0)))
+    th = math.acos(c)
+    a = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = 0.5 * np.linalg.norm(a)
+    if s < 1e-10:
+        if c > 0:
+            return 0.5 * a
+        d = np.sqrt(np.maximum(0.0, 0.5 * (np.diag(R) + 1.0)))
+        d[1] = -d[1] if R[0, 1] + R[1, 0] < 0 else d[1]
+        d[2] = -d[2] if R[0, 2] + R[2, 0] < 0 else d[2]
+        return th * d
+    return (0.5 * th / s) * a
+
+
+def pnp_refine(X, kp, K, dist, R0, t0, w=None, min_weight: float = 0.0, max_iters: int = 50):
+    """Minimise sum_k |project(R X_k + t) - kp_k|^2 over the pose by Levenberg-Marquardt from the
+    prior (R0, t0), in float64 — the same cost cv2.solvePnP(SOLVEPNP_ITERATIVE,
+    useExtrinsicGuess=True) minimises (call site being replaced: estimate_camera_pose,
+    model/Fr5_model_train.ipynb:4707-4753). Points with w < min_weight or non-finite kp are
+    dropped; fewer than 4 valid points (the reference's refusal, :4728) returns the prior.
+    X (K,3), kp (K,2). Returns (rvec, tvec, rms_px, status) with status bits as the kernel."""
+    X = np.asarray(X, dtype=np.float64)
+    kp = np.asarray(kp, dtype=np.float64)
+    R, t = np.asarray(R0, dtype=np.float64).copy(), np.asarray(t0, dtype=np.float64).reshape(3).copy()
+    ok = np.isfinite(kp).all(axis=1)
+    if w is not None:
+        ok &= np.asarray(w, dtype=np.float64) >= min_weight
+    n = int(ok.sum())
+    if n < 4:
+        return rvec_from_matrix(R), t, float("nan"), 0
+    Xv, kv = X[ok], kp[ok]
+
+    def residual(Rr, tt):
+        return (project_points(Xv, Rr, tt, K, dist) - kv).reshape(-1)
+
+    def jacobian(Rr, tt, eps=1e-7):
+        J = np.zeros((2 * n, 6))
+        for j in range(6):
+            d = np.zeros(6)
+            d[j] = eps
+            Rp, Rm = rodrigues(d[:3]) @ Rr, rodrigues(-d[:3]) @ Rr
+            J[:, j] = (residual(Rp, tt + d[3:]) - residual(Rm, tt - d[3:])) / (2 * eps)
+        return J
+
+    lam, status = 1e-3, 1
+    r = residual(R, t)
+    cost = float(r @ r)
+    for _ in range(max_iters):
+        J = jacobian(R, t)
+        H, g = J.T @ J, J.T @ r
+        accepted = False
+        for _try in range(8):
+            try:
+                d = np.linalg.solve(H + lam * np.diag(np.diag(H)) + 1e-12 * np.eye(6), -g)
+            except np.linalg.LinAlgError:
+                lam *= 10
+                continue
+            Rn, tn = rodrigues(d[:3]) @ R, t + d[3:]
+            rn = residual(Rn, tn)
+            cn = float(rn @ rn)
+            if cn <= cost:
+                small = (cost - cn) <= 1e-14 * cost + 1e-20
+                R, t, r, cost, lam, accepted = Rn, tn, rn, cn, max(lam * 0.1, 1e-12), True
+                if small:
+                    status |= 2
+                break
+            lam *= 10
+        if not accepted or (status & 2):
+            status |= 2
+            break
+    if 0.25 < float(t @ t) < 25.0:
+        status |= 4
+    return rvec_from_matrix(R), t, math.sqrt(cost / n), status

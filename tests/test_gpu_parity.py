@@ -556,3 +556,49 @@ def test_training_step_losses_have_correct_gradients(mv):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
+
+
+# ===================================================================== camera-pose refinement (PnP)
+@pytest.mark.parametrize("distortion", [False, True])
+def test_pnp_refine_vs_float64_lm(mv, distortion):
+    rng = np.random.default_rng(61)
+    V, B = 3, 24
+    chain = mv.Chain.builtin("fr3")
+    K = chain.n_points
+    true_rig = mv.CameraRig.synthetic_ring_for("fr3", V, distortion=distortion)
+    Rv = np.stack([np.asarray(mv.view_rotation("fr3", "view1"))] * V).astype(np.float32)
+    q = torch.from_numpy(rng.uniform(-2, 2, (B, 7)).astype(np.float32)).to(DEV)
+    X = mv.forward_kinematics(chain, q, Rv)                                    # (B,V,K,3) object points
+    kp = mv.project_points(X, true_rig) + torch.from_numpy(rng.normal(0, 0.7, (B, V, K, 2)).astype(np.float32)).to(DEV)
+    w = torch.from_numpy(rng.uniform(0.3, 1.0, (B, V, K)).astype(np.float32)).to(DEV)
+    w[0, 0, :5] = 0.1           # only 3 confident points left -> refused, prior returned
+    kp[1, 1, 2] = float("nan")  # dropped point
+    # prior = true pose perturbed by ~3 degrees / 5 cm (what an ArUco prior is to the true pose)
+    prior = mv.CameraRig(true_rig.K.copy(), true_rig.dist.copy(),
+                         np.stack([O.rodrigues(rng.normal(0, 0.05, 3)) @ R for R in true_rig.R]),
+                         true_rig.t + rng.normal(0, 0.05, true_rig.t.shape))
+    rvec, tvec, rms, st = mv.pnp_refine(X, kp, prior, w, min_weight=0.2, max_iters=30)
+    rvec, tvec, rms, st = _to_np32(rvec), _to_np32(tvec), _to_np32(rms), st.cpu().numpy()
+    Xn, kpn, wn = _to_np32(X).astype(np.float64), _to_np32(kp).astype(np.float64), _to_np32(w)
+    pk = prior.packed()  # the float32 camera records the kernel sees
+    for b in range(B):
+        for v in range(V):
+            R0, t0 = pk[v, 0:9].reshape(3, 3).astype(np.float64), pk[v, 9:12].astype(np.float64)
+            Kc = np.array([[pk[v, 12], 0, pk[v, 14]], [0, pk[v, 13], pk[v, 15]], [0, 0, 1]], dtype=np.float64)
+            rv_o, t_o, rms_o, st_o = O.pnp_refine(Xn[b, v], kpn[b, v], Kc, pk[v, 16:21].astype(np.float64), R0, t0, wn[b, v], 0.2)
+            assert (st[b, v] & 1) == (st_o & 1)
+            if st_o & 1:
+                assert st[b, v] & 2 and st[b, v] & 4
+                np.testing.assert_allclose(rvec[b, v], rv_o, atol=2e-4)
+                np.testing.assert_allclose(tvec[b, v], t_o, atol=2e-4)
+                assert abs(rms[b, v] - rms_o) <= 2e-3 * max(1.0, rms_o)
+            else:
+                np.testing.assert_allclose(rvec[b, v], O.rvec_from_matrix(R0), atol=1e-6)
+                np.testing.assert_allclose(tvec[b, v], t0, atol=1e-7)
+                assert np.isnan(rms[b, v])
+    assert st[0, 0] == 0 and (st[1, 1] & 1)
+    # refinement recovers the true pose to the noise level from a 3-degree / 5-cm prior
+    true_rv = np.stack([O.rvec_from_matrix(R) for R in true_rig.R])
+    good = (st & 1).astype(bool)
+    er, et = np.abs(rvec - true_rv[None])[good], np.abs(tvec - true_rig.t[None])[good]
+    assert np.median(er) < 1e-2 and er.max() < 0.1 and np.median(et) < 1.5e-2 and et.max() < 0.15  # 8 points, 0.7 px noise

@@ -194,6 +194,14 @@ assert g["X"].shape == (2, 3, 2) and g["i"].shape == (2, 3) and g["i"].dtype == 
 for r in range(ws):
     assert torch.equal(g["X"][r], torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * r)
     assert torch.equal(g["i"][r], torch.arange(3, dtype=torch.int32) - r)
+ring = mvgeo.sharding.ResultRing({{"X": ((3, 2), torch.float32), "n": ((3,), torch.int32)}}, 4, "cpu")
+for k in range(3):  # a 3-batch job
+    ring.slot[k]["X"].fill_(10.0 * rank + k); ring.slot[k]["n"].fill_(100 * rank + k)
+allr = ring.final_gather(3)
+assert allr.shape == (ws, 3, 9)
+for r in range(ws):
+    for k in range(3):
+        assert torch.all(allr[r, k, :6] == 10.0 * r + k) and torch.all(allr[r, k, 6:].view(torch.int32) == 100 * r + k)
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """

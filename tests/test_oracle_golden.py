@@ -296,3 +296,29 @@ def test_heatmap_mse_restatement():
     l.backward()
     assert abs(loss - float(l)) < 1e-12
     np.testing.assert_allclose(grad, p.grad.numpy(), atol=1e-15)
+
+
+# ------------------------------------------------------------------ camera-pose refinement
+def test_pnp_refine_oracle_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    for trial in range(6):
+        Kc, dist = G["zedx_K"][trial % 8], G["zedx_dist"][trial % 8]
+        rv_true = rng.uniform(-0.8, 0.8, 3)
+        t_true = np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(1.2, 2.5)])
+        X = O.fk_fr3(rng.uniform(-2, 2, 7), "view1").astype(np.float64) + rng.normal(0, 0.02, (8, 3))
+        kp = O.project_points(X, O.rodrigues(rv_true), t_true, Kc, dist) + rng.normal(0, 0.5, (8, 2))
+        rv0, t0 = rv_true + rng.normal(0, 0.05, 3), t_true + rng.normal(0, 0.05, 3)
+        rv, tv, rms, st = O.pnp_refine(X, kp, Kc, dist, O.rodrigues(rv0), t0)
+        ok, rv_cv, t_cv = cv2.solvePnP(X, kp, Kc, dist, rv0.reshape(3, 1).copy(), t0.reshape(3, 1).copy(), True, cv2.SOLVEPNP_ITERATIVE)
+        assert ok and (st & 3) == 3 and (st & 4)
+        # same minimum of the same cost: cv2's LM stops at its own tolerance, ours goes to machine precision
+        np.testing.assert_allclose(rv, rv_cv.ravel(), atol=2e-4)
+        np.testing.assert_allclose(tv, t_cv.ravel(), atol=2e-4)
+        e_cv = O.project_points(X, O.rodrigues(rv_cv.ravel()), t_cv.ravel(), Kc, dist) - kp
+        assert rms <= math.sqrt(np.mean(np.sum(e_cv ** 2, axis=1))) + 1e-9
+        np.testing.assert_allclose(O.rvec_from_matrix(O.rodrigues(rv_true)), rv_true, atol=1e-12)
+    rv, tv, rms, st = O.pnp_refine(X[:3], kp[:3], Kc, dist, O.rodrigues(rv0), t0)   # < 4 points: the prior comes back
+    assert st == 0 and np.isnan(rms)
+    np.testing.assert_allclose(rv, rv0, atol=1e-12)
+    np.testing.assert_allclose(tv, t0, atol=1e-12)

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "mvgeo_triangulate": ([_vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp], _i),
     "mvgeo_fk": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _i, _vp, _vp], _i),
     "mvgeo_project": ([_vp, _i, _vp, _i64, _i, _i, _vp, _vp], _i),
+    "mvgeo_undistort_points": ([_vp, _vp, _i64, _i, _i, _i, _vp, _vp], _i),
     "mvgeo_fk_reproj_fwd": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_fk_reproj_bwd": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp], _i),
     "mvgeo_pnp_refine": ([_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),

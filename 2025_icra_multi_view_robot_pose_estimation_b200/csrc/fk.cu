@@ -319,6 +319,30 @@ __global__ void __launch_bounds__(kFkThreads)
   }
 }
 
+// cv2.undistortPoints(src, K, dist, P=K): pixel -> normalised -> fixed-point inversion of the
+// Brown-Conrady model (OpenCV's default: 5 iterations) -> pixel of the ideal pinhole camera.
+__global__ void __launch_bounds__(kFkThreads) undistort_kernel(const float* __restrict__ kp,
+                                                               const mvgeo_camera* __restrict__ cams, int64_t n,
+                                                               int V, int K, int iters, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kFkThreads + threadIdx.x;
+  if (i >= n) return;
+  const int v = (int)((i / K) % V);
+  const mvgeo_camera& c = cams[v];
+  const float k1 = c.dist[0], k2 = c.dist[1], p1 = c.dist[2], p2 = c.dist[3], k3 = c.dist[4];
+  const float x0 = (kp[2 * i] - c.cx) / c.fx, y0 = (kp[2 * i + 1] - c.cy) / c.fy;
+  float x = x0, y = y0;
+  for (int it = 0; it < iters; ++it) {
+    const float r2 = x * x + y * y;
+    const float icdist = 1.0f / (1.0f + ((k3 * r2 + k2) * r2 + k1) * r2);
+    const float dx = 2.0f * p1 * x * y + p2 * (r2 + 2.0f * x * x);
+    const float dy = p1 * (r2 + 2.0f * y * y) + 2.0f * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  out[2 * i] = c.fx * x + c.cx;
+  out[2 * i + 1] = c.fy * y + c.cy;
+}
+
 // Deterministic fixed-order sum of n floats into out[0]: one CTA, strided per-thread partials,
 // then a shared-memory tree.
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
@@ -418,6 +442,18 @@ extern "C" int mvgeo_project(const float* X, int x_per_view, const mvgeo_camera*
   const int64_t n = B * V * K;
   const unsigned grid = (unsigned)((n + kFkThreads - 1) / kFkThreads);
   project_kernel<<<grid, kFkThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(X, x_per_view, cams, B, V, K, uv);
+  MVGEO_CHECK_LAUNCH();
+  return MVGEO_OK;
+}
+
+extern "C" int mvgeo_undistort_points(const float* kp, const mvgeo_camera* cams, int64_t B, int V, int K, int iters,
+                                      float* out, void* stream) {
+  if (B < 0 || V < 1 || V > MVGEO_MAX_VIEWS || K < 1 || iters < 0 || iters > 100) return MVGEO_EINVAL;
+  if (B == 0) return MVGEO_OK;
+  if (!kp || !cams || !out) return MVGEO_ENULL;
+  const int64_t n = B * V * K;
+  const unsigned grid = (unsigned)((n + kFkThreads - 1) / kFkThreads);
+  undistort_kernel<<<grid, kFkThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(kp, cams, n, V, K, iters, out);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }

@@ -186,6 +186,22 @@ def project_points(X: torch.Tensor, cams) -> torch.Tensor:
     return uv
 
 
+def undistort_points(kp: torch.Tensor, cams, iters: int = 5) -> torch.Tensor:
+    """cv2.undistortPoints(kp, K, dist, P=K) per view: kp (B,V,K,2) pixels of the distorted image ->
+    pixels of the ideal pinhole camera (what cv2.undistort does to whole images, MvRoPose_FR3.py:212)."""
+    lib = _lib.load()
+    kp = _need_cuda(kp, "kp", torch.float32)
+    cams_t = cameras_to_device(cams, kp.device)
+    V = int(cams_t.shape[0])
+    if kp.dim() != 4 or kp.shape[1] != V or kp.shape[-1] != 2:
+        raise ValueError("kp must be (B, V, K, 2) with V matching the rig")
+    out = torch.empty_like(kp)
+    with torch.cuda.device(kp.device):
+        _lib.check(lib.mvgeo_undistort_points(kp.data_ptr(), cams_t.data_ptr(), kp.shape[0], V, kp.shape[2], int(iters),
+                                              out.data_ptr(), _stream(kp.device)), "mvgeo_undistort_points")
+    return out
+
+
 class _FKReprojLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, chain, cams_t, gt_uv, R_view, w, lam):

@@ -170,6 +170,14 @@ int mvgeo_fk(const mvgeo_chain* chain, const float* q, int64_t B,
 int mvgeo_project(const float* X, int x_per_view, const mvgeo_camera* cams,
                   int64_t B, int V, int K, float* uv, void* stream);
 
+/* Inverse of the distortion: cv2.undistortPoints(kp, K, dist, P=K) (OpenCV's fixed-point iteration,
+ * `iters` = 5 is its default), so key-points decoded from RAW (not cv2.undistort-ed) images can be
+ * triangulated with pinhole projection matrices. The reference undistorts whole images instead
+ * (cv2.undistort, model/MvRoPose_FR3.py:212, DIP_REAL.py:105); this is the per-key-point equivalent.
+ *   kp, out  [B, V, K, 2] f32 pixels;  cams [V] (intrinsics and dist are used) */
+int mvgeo_undistort_points(const float* kp, const mvgeo_camera* cams, int64_t B, int V, int K, int iters,
+                           float* out, void* stream);
+
 /* ------------------------------------- FK + reprojection loss, fwd / bwd
  * Replaces RobotPoseNet.forward's FK -> project chain plus the FK-consistency term of
  * robot_pose_loss (model/MV-model.ipynb:915-950), and makes it differentiable:

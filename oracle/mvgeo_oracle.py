@@ -587,3 +587,20 @@ def pnp_refine(X, kp, K, dist, R0, t0, w=None, min_weight: float = 0.0, max_iter
     if 0.25 < float(t @ t) < 25.0:
         status |= 4
     return rvec_from_matrix(R), t, math.sqrt(cost / n), status
+
+
+def undistort_points(kp, K, dist, iters: int = 5) -> np.ndarray:
+    """cv2.undistortPoints(kp, K, dist, P=K): OpenCV's fixed-point inversion of the Brown-Conrady
+    model (5 iterations by default), float64. kp (...,2) pixels -> (...,2) pixels."""
+    kp = np.asarray(kp, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    k1, k2, p1, p2, k3 = (float(c) for c in np.asarray(dist, dtype=np.float64).reshape(-1)[:5])
+    x0, y0 = (kp[..., 0] - K[0, 2]) / K[0, 0], (kp[..., 1] - K[1, 2]) / K[1, 1]
+    x, y = x0.copy(), y0.copy()
+    for _ in range(iters):
+        r2 = x * x + y * y
+        icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2)
+        dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+        dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+        x, y = (x0 - dx) * icdist, (y0 - dy) * icdist
+    return np.stack([K[0, 0] * x + K[0, 2], K[1, 1] * y + K[1, 2]], axis=-1)

@@ -602,3 +602,67 @@ def test_pnp_refine_vs_float64_lm(mv, distortion):
     good = (st & 1).astype(bool)
     er, et = np.abs(rvec - true_rv[None])[good], np.abs(tvec - true_rig.t[None])[good]
     assert np.median(er) < 1e-2 and er.max() < 0.1 and np.median(et) < 1.5e-2 and et.max() < 0.15  # 8 points, 0.7 px noise
+
+
+# ============================================ randomized property sweep (shapes, dtypes, ties, modes)
+def test_decode_random_shapes_property_sweep(mv):
+    """60 random (shape, dtype, value distribution, mode) cases incl. 1x1 maps, 16-byte-sized maps,
+    odd sizes (generic kernel), heavy ties, +-inf, NaN: arg-max bit-exact, soft-arg-max <= 1e-3 px."""
+    rng = np.random.default_rng(2025)
+    dtypes = [torch.float32, torch.bfloat16, torch.float16]
+    shapes = [(1, 1), (1, 8), (2, 4), (4, 4), (3, 5), (16, 16), (8, 24), (33, 17), (40, 64), (64, 48), (100, 100), (128, 128)]
+    for case in range(60):
+        H, W = shapes[case % len(shapes)] if case < 36 else (int(rng.integers(1, 90)), int(rng.integers(1, 90)))
+        n = int(rng.integers(1, 40))
+        dtype = dtypes[case % 3]
+        kind = case % 5
+        if kind == 0:
+            a = rng.normal(0, 1, (n, H, W))
+        elif kind == 1:
+            a = rng.integers(0, 3, (n, H, W)) * 0.5                     # heavy ties
+        elif kind == 2:
+            a = rng.uniform(-1, 1, (n, H, W))
+            a[rng.uniform(size=a.shape) < 0.02] = np.inf                 # several +inf: first wins
+        elif kind == 3:
+            a = rng.uniform(0, 1, (n, H, W))
+            a[rng.uniform(size=a.shape) < 0.01] = np.nan                 # NaN maximal
+            a[0] = -np.inf
+        else:
+            a = np.full((n, H, W), -2.5) + (rng.uniform(size=(n, H, W)) < 0.05) * 3.0
+        t, seen = _as_dtype(a.astype(np.float32), dtype)
+        beta = float(rng.choice([5.0, 40.0, 300.0]))
+        for soft, radius in (("global", 0), ("window", int(rng.integers(0, 16)))):
+            r = mv.decode_heatmaps(t, None, soft=soft, beta=beta, window_radius=radius)
+            ref_idx, ref_peak = O.argmax_first(seen)
+            np.testing.assert_array_equal(r.idx.cpu().numpy(), ref_idx, err_msg=f"case {case} {H}x{W} {dtype} {soft}")
+            pk = _to_np32(r.peak)
+            assert np.array_equal(np.isnan(pk), np.isnan(ref_peak)) and np.array_equal(pk[~np.isnan(pk)], ref_peak[~np.isnan(ref_peak)])
+            if kind in (0, 1, 4):  # finite maps: compare the sub-pixel estimate
+                ref = O.soft_argmax(seen, beta, soft, radius)
+                assert np.abs(_to_np32(r.kp_soft) - ref).max() < 1e-3, (case, H, W, dtype, soft, beta)
+
+
+def test_undistort_points_vs_oracle_and_cv2(mv):
+    rng = np.random.default_rng(14)
+    rig = mv.CameraRig.synthetic_ring(4, distortion=True)
+    kp = np.stack([rng.uniform(0, 1920, (16, 4, 9)), rng.uniform(0, 1200, (16, 4, 9))], axis=-1).astype(np.float32)
+    und = _to_np32(mv.undistort_points(torch.from_numpy(kp).to(DEV), rig))
+    pk = rig.packed()
+    for v in range(4):
+        Kc = np.array([[pk[v, 12], 0, pk[v, 14]], [0, pk[v, 13], pk[v, 15]], [0, 0, 1]], dtype=np.float64)
+        ref = O.undistort_points(kp[:, v].astype(np.float64), Kc, pk[v, 16:21].astype(np.float64))
+        np.testing.assert_allclose(und[:, v], ref, rtol=1e-6, atol=2e-3)
+        try:
+            import cv2
+            ref2 = cv2.undistortPoints(kp[:, v].reshape(-1, 1, 2).astype(np.float64), Kc, pk[v, 16:21].astype(np.float64), P=Kc)
+            np.testing.assert_allclose(und[:, v].reshape(-1, 2), ref2.reshape(-1, 2), rtol=1e-6, atol=2e-3)
+        except ImportError:
+            pass
+    # distorted detections -> undistort -> triangulate == the 3-D points (pinhole P only)
+    X = (rng.uniform(-0.5, 0.5, (16, 9, 3)) + [0, 0, 0.4]).astype(np.float32)
+    kp_d = mv.project_points(torch.from_numpy(X).to(DEV), rig)                       # with distortion
+    P = torch.from_numpy(rig.projection_matrices()).to(DEV)
+    Xt = _to_np32(mv.triangulate(mv.undistort_points(kp_d, rig, iters=10), P)[0])
+    assert np.abs(Xt - X).max() < 5e-5
+    Xraw = _to_np32(mv.triangulate(kp_d, P)[0])
+    assert np.abs(Xraw - X).max() > 10 * np.abs(Xt - X).max()  # without it the distortion shows up in 3-D

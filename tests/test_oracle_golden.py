@@ -322,3 +322,17 @@ def test_pnp_refine_oracle_vs_cv2():
     assert st == 0 and np.isnan(rms)
     np.testing.assert_allclose(rv, rv0, atol=1e-12)
     np.testing.assert_allclose(tv, t0, atol=1e-12)
+
+
+def test_undistort_points_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for i in range(8):
+        Kc, dist = G["zedx_K"][i], G["zedx_dist"][i]
+        kp = np.stack([rng.uniform(0, 1920, 50), rng.uniform(0, 1200, 50)], axis=1)
+        ref = cv2.undistortPoints(kp.reshape(-1, 1, 2), Kc, dist, P=Kc).reshape(-1, 2)
+        np.testing.assert_allclose(O.undistort_points(kp, Kc, dist), ref, rtol=0, atol=1e-9)
+        # round trip: distort(undistort(p)) == p (what makes raw-image key-points triangulable)
+        und = O.undistort_points(kp, Kc, dist, iters=20)
+        xn = np.concatenate([(und - [Kc[0, 2], Kc[1, 2]]) / [Kc[0, 0], Kc[1, 1]], np.ones((50, 1))], axis=1)
+        np.testing.assert_allclose(O.project_points(xn, np.eye(3), np.zeros(3), Kc, dist), kp, atol=1e-6)

@@ -7,8 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# MVGEO_LIB overrides the path for kernel-development A/B builds only
-LIB_PATH = os.environ.get("MVGEO_LIB") or os.path.join(_HERE, "libmvgeo.so")
+LIB_PATH = os.path.join(_HERE, "libmvgeo.so")
 
 MAX_JOINTS = 8
 MAX_VIEWS = 16
@@ -62,6 +61,7 @@ _SIGNATURES = {
     "mvgeo_chain_builtin": ([_i, C.POINTER(ChainStruct)], _i),
     "mvgeo_decode": ([_vp, _i, _i64, _i, _i, _d, _d, _i, _f, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_triangulate": ([_vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp], _i),
+    "mvgeo_quat_mean": ([_vp, _vp, _i64, _i, _vp, _vp], _i),
     "mvgeo_fk": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _i, _vp, _vp], _i),
     "mvgeo_project": ([_vp, _i, _vp, _i64, _i, _i, _vp, _vp], _i),
     "mvgeo_undistort_points": ([_vp, _vp, _i64, _i, _i, _i, _vp, _vp], _i),

@@ -26,7 +26,6 @@
 //   * maps whose slice-maxima table cannot fit one CTA (> ~2.4 MB) are split over a thread-block
 //     cluster of <= 8 CTAs and combined through distributed shared memory.
 #include <cooperative_groups.h>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -614,10 +613,7 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
     //   large maps  -> one group; split over a cluster only when the slice-maxima table
     //                  (2 bytes per kTmaU chunks) cannot fit one CTA.
     const int64_t chunks = map_bytes / 16;
-    const char* eg = getenv("MVGEO_DECODE_GROUPS");  // kernel-development override
-    if (eg) groups = atoi(eg);
-    else groups = map_bytes <= 112 * 1024 ? 4 : 1;
-    if (groups != 1 && groups != 2 && groups != 4) return MVGEO_EINVAL;
+    groups = map_bytes <= 112 * 1024 ? 4 : 1;
     const int64_t tile = (int64_t)(kDecThreads / groups) * kTmaU;
     int splits = 1;
     while (splits < kMaxSplits && ((chunks + splits - 1) / splits + tile - 1) / tile * kDecThreads * 2 > kMaxTableBytes)

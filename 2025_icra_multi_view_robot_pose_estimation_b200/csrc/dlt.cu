@@ -213,9 +213,112 @@ __global__ void __launch_bounds__(kDltThreads)
   }
 }
 
+// Quaternion averaging: the eigenvector of the LARGEST eigenvalue of M = sum_i w_i q_i q_i^T
+// (average_quaternion, dataset/Fr5_preprocessing.py:57-65 = dataset/Franka_research3_preprocessing.py:
+// 59-67; np.linalg.eigh there). Same 4-lanes-per-problem layout and the same Jacobi + FP64
+// correction as the triangulation above, with arg-max instead of arg-min. The sign (arbitrary in
+// eigh) is fixed to the hemisphere of the group's first quaternion.
+__global__ void __launch_bounds__(kDltThreads)
+    quat_mean_kernel(const float* __restrict__ q, const float* __restrict__ w, int64_t G, int N,
+                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 3;
+  int64_t gid = (int64_t)blockIdx.x * (kDltThreads / 4) + (threadIdx.x >> 2);
+  const bool active = gid < G;
+  if (!active) gid = G - 1;
+  const float* qg = q + gid * (int64_t)N * 4;
+  double Mc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < N; ++i) {
+    const double wt = w ? (double)w[gid * (int64_t)N + i] : 1.0;
+    const double a[4] = {(double)qg[4 * i], (double)qg[4 * i + 1], (double)qg[4 * i + 2], (double)qg[4 * i + 3]};
+    const double aj = lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Mc[r] += wt * a[r] * aj;
+  }
+  double diag = lane == 0 ? Mc[0] : lane == 1 ? Mc[1] : lane == 2 ? Mc[2] : Mc[3];
+  double tr = diag + xor4(diag, 1);
+  tr += xor4(tr, 2);
+  const double inv_tr = tr > 0.0 ? 1.0 / tr : 0.0;
+  double Md[4];
+  float A[4], Vc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Md[i] = Mc[i] * inv_tr;
+    A[i] = (float)Md[i];
+    Vc[i] = (i == lane) ? 1.0f : 0.0f;
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < kDltSweeps; ++sweep) {
+    jacobi_rotate<0, 1>(A, Vc, lane);
+    jacobi_rotate<2, 3>(A, Vc, lane);
+    jacobi_rotate<0, 2>(A, Vc, lane);
+    jacobi_rotate<1, 3>(A, Vc, lane);
+    jacobi_rotate<0, 3>(A, Vc, lane);
+    jacobi_rotate<1, 2>(A, Vc, lane);
+  }
+  const float lam = lane == 0 ? A[0] : lane == 1 ? A[1] : lane == 2 ? A[2] : A[3];
+  float lmax = lam;
+  int imax = lane;
+#pragma unroll
+  for (int m = 1; m < 4; m <<= 1) {
+    const float ol = xor4(lmax, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, imax, m, 4);
+    if (ol > lmax || (ol == lmax && oi < imax)) {
+      lmax = ol;
+      imax = oi;
+    }
+  }
+  double x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = (double)shfl4(Vc[i], imax);
+  const double xj = lane == 0 ? x[0] : lane == 1 ? x[1] : lane == 2 ? x[2] : x[3];
+  double Mx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = Md[i] * xj;
+    t += xor4(t, 1);
+    t += xor4(t, 2);
+    Mx[i] = t;
+  }
+  const double xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+  const double lam0 = (x[0] * Mx[0] + x[1] * Mx[1] + x[2] * Mx[2] + x[3] * Mx[3]) / xx;
+  double coef = 0.0;
+  if (lane != imax) {
+    double vr = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vr += (double)Vc[i] * (Mx[i] - lam0 * x[i]);
+    const double den = lam0 - (double)lam;
+    if (fabs(den) > 1e-12) coef = vr / den;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = coef * (double)Vc[i];
+    t += xor4(t, 1);
+    t += xor4(t, 2);
+    x[i] += t;
+  }
+  const double nrm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  const double d0 = x[0] * qg[0] + x[1] * qg[1] + x[2] * qg[2] + x[3] * qg[3];
+  const double sgn = (d0 < 0.0 ? -1.0 : 1.0) / (nrm > 0.0 ? nrm : 1.0);
+  if (active) {
+    const double xo = lane == 0 ? x[0] : lane == 1 ? x[1] : lane == 2 ? x[2] : x[3];
+    out[4 * gid + lane] = (tr > 0.0 && N > 0) ? (float)(xo * sgn) : __int_as_float(0x7fc00000);
+  }
+}
+
 }  // namespace mvgeo
 
 using namespace mvgeo;
+
+extern "C" int mvgeo_quat_mean(const float* q, const float* w, int64_t G, int N, float* out, void* stream) {
+  if (G < 0 || N < 1) return MVGEO_EINVAL;
+  if (G == 0) return MVGEO_OK;
+  if (!q || !out) return MVGEO_ENULL;
+  const int per_cta = kDltThreads / 4;
+  const unsigned grid = (unsigned)((G + per_cta - 1) / per_cta);
+  quat_mean_kernel<<<grid, kDltThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q, w, G, N, out);
+  MVGEO_CHECK_LAUNCH();
+  return MVGEO_OK;
+}
 
 extern "C" int mvgeo_triangulate(const float* kp, const float* w, const float* P, int64_t B, int V, int K,
                                  float min_weight, int weighted, float* X, float* resid, int32_t* n_views,

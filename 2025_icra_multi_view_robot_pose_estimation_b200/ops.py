@@ -134,6 +134,24 @@ def triangulate(kp: torch.Tensor, P: torch.Tensor, w: Optional[torch.Tensor] = N
     return X, resid, nv
 
 
+def quat_mean(q: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched average_quaternion (dataset/Fr5_preprocessing.py:57-65): q (G, N, 4) -> (G, 4) unit
+    quaternions (largest eigenvector of sum w q q^T), sign in the hemisphere of q[:, 0]."""
+    lib = _lib.load()
+    q = _need_cuda(q, "q", torch.float32)
+    if q.dim() != 3 or q.shape[-1] != 4:
+        raise ValueError("q must be (G, N, 4)")
+    if w is not None:
+        w = _need_cuda(w, "w", torch.float32)
+        if tuple(w.shape) != tuple(q.shape[:2]):
+            raise ValueError("w must be (G, N)")
+    out = torch.empty((q.shape[0], 4), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.mvgeo_quat_mean(q.data_ptr(), _ptr(w), q.shape[0], q.shape[1], out.data_ptr(), _stream(q.device)),
+                   "mvgeo_quat_mean")
+    return out
+
+
 # ------------------------------------------------------------------------ FK and projection
 def _view_rot(R_view, dev, V_expected=None):
     if R_view is None:

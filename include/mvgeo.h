@@ -143,6 +143,13 @@ int mvgeo_triangulate(const float* kp, const float* w, const float* P,
                       int64_t B, int V, int K, float min_weight, int weighted,
                       float* X, float* resid, int32_t* n_views, void* stream);
 
+/* Quaternion averaging with the same register-resident 4x4 symmetric eigen-solver: the unit
+ * eigenvector of the largest eigenvalue of sum_i w_i q_i q_i^T — average_quaternion,
+ * dataset/Fr5_preprocessing.py:57-65 (= dataset/Franka_research3_preprocessing.py:59-67), which the
+ * ArUco extrinsics pipeline applies per marker. Sign: hemisphere of the group's first quaternion.
+ *   q [G, N, 4] f32 (any fixed component order), w [G, N] f32 (nullable), out [G, 4] f32 */
+int mvgeo_quat_mean(const float* q, const float* w, int64_t G, int N, float* out, void* stream);
+
 /* --------------------------------------------------- forward kinematics
  * Replaces angle_to_joint_coordinate (FR3 model/MvRoPose_FR3.py:90-131; Fr5
  * model/Fr5_model_train.ipynb:256-288), forward_kinematics (Meca500

@@ -604,3 +604,15 @@ def undistort_points(kp, K, dist, iters: int = 5) -> np.ndarray:
         dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
         x, y = (x0 - dx) * icdist, (y0 - dy) * icdist
     return np.stack([K[0, 0] * x + K[0, 2], K[1, 1] * y + K[1, 2]], axis=-1)
+
+
+def average_quaternion(quaternions, weights=None) -> np.ndarray:
+    """dataset/Fr5_preprocessing.py:57-65 (average_quaternion): M = sum q q^T, eigenvector of the
+    largest eigenvalue (np.linalg.eigh), normalised. Sign is arbitrary in the reference."""
+    M = np.zeros((4, 4))
+    for i, q in enumerate(np.asarray(quaternions, dtype=np.float64)):
+        q = q.reshape(4, 1)
+        M += (1.0 if weights is None else float(weights[i])) * (q @ q.T)
+    eigvals, eigvecs = np.linalg.eigh(M)
+    avg = eigvecs[:, np.argmax(eigvals)]
+    return avg / np.linalg.norm(avg)

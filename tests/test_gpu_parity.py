@@ -666,3 +666,21 @@ def test_undistort_points_vs_oracle_and_cv2(mv):
     assert np.abs(Xt - X).max() < 5e-5
     Xraw = _to_np32(mv.triangulate(kp_d, P)[0])
     assert np.abs(Xraw - X).max() > 10 * np.abs(Xt - X).max()  # without it the distortion shows up in 3-D
+
+
+def test_quat_mean_vs_reference_eigh(mv):
+    rng = np.random.default_rng(77)
+    G_, N = 50, 12
+    base = rng.normal(size=(G_, 4))
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    q = base[:, None, :] + rng.normal(0, 0.05, (G_, N, 4))           # detections scattered around a pose
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    q[::3, 1::2] *= -1.0                                              # q and -q are the same rotation
+    w = rng.uniform(0.2, 1.0, (G_, N))
+    for wt in (None, w):
+        out = _to_np32(mv.quat_mean(torch.from_numpy(q.astype(np.float32)).to(DEV),
+                                    None if wt is None else torch.from_numpy(wt.astype(np.float32)).to(DEV)))
+        for g in range(G_):
+            ref = O.average_quaternion(q[g].astype(np.float32), None if wt is None else wt[g].astype(np.float32))
+            assert abs(abs(float(out[g] @ ref)) - 1.0) < 1e-6 and abs(np.linalg.norm(out[g]) - 1.0) < 1e-6
+            assert out[g] @ q[g, 0] >= 0                              # sign: hemisphere of the first sample

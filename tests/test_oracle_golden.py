@@ -336,3 +336,18 @@ def test_undistort_points_vs_cv2():
         und = O.undistort_points(kp, Kc, dist, iters=20)
         xn = np.concatenate([(und - [Kc[0, 2], Kc[1, 2]]) / [Kc[0, 0], Kc[1, 1]], np.ones((50, 1))], axis=1)
         np.testing.assert_allclose(O.project_points(xn, np.eye(3), np.zeros(3), Kc, dist), kp, atol=1e-6)
+
+
+def test_average_quaternion_matches_reference_function():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    import importlib.util, types
+    src = open(os.path.join(ref_loader.REF_ROOT, "dataset", "Fr5_preprocessing.py")).read()
+    ns = dict(np=np)
+    exec(ref_loader._extract_defs(src, ["average_quaternion"]), ns)
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=(9, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    ref = ns["average_quaternion"](q)
+    got = O.average_quaternion(q)
+    assert abs(abs(ref @ got) - 1.0) < 1e-12

@@ -40,6 +40,6 @@ for _ in range(30):
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 med, best = statistics.median(ts), min(ts)
 chk = int(idx.sum()), float(kps.double().sum())
-tag = os.path.basename(os.environ.get('MVGEO_LIB', 'default')) + " g=" + os.environ.get('MVGEO_DECODE_GROUPS', '-')
+tag = "libmvgeo"
 print(f"{tag:28s} {B}x{V}x{K}x{H}x{W} {a[5] if len(a)>5 else 'bf16'} {mode:6s} "
       f"median {med*1e3:8.1f} us  {nbytes/med/1e6:8.1f} GB/s   best {nbytes/best/1e6:8.1f} GB/s  chk={chk}")

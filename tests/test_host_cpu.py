@@ -216,3 +216,23 @@ def test_gather_frames_gloo_world_size_2(mv, tmp_path):
     for r, p in enumerate(procs):
         out, err = p.communicate(timeout=600)
         assert p.returncode == 0 and f"OK {r}" in out, err[-2000:]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the path) prints the contract's JSON line."""
+    import json
+
+    env = dict(os.environ, MVGEO_BENCH_REF_SECONDS="0.5")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["metric"] == "frames/s decode+triangulate+FK" and d["config"]["workload"].startswith("C2")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+    # other ranks of a torchrun launch exit 0 without work
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                         capture_output=True, text=True, timeout=120, env=dict(env, RANK="3", WORLD_SIZE="8"), cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -190,11 +190,14 @@ __device__ __forceinline__ uint16_t to_carrier(float m) {
   return Elem<DT>::pack(m);
 }
 
-// Everything after the streaming pass, for one group of NW consumer warps (NT = 32 NW threads,
-// barrier `bar`, `gt` = thread index in the group): resolve the first maximal element inside the
-// winning slice, reduce (value, index) over the group and the cluster, run the soft-arg-max
-// pass, write the outputs. smax[t*NT + gt] = maximum of thread gt's slice of tile t.
-template <int DT, int MODE, int NW, int U>
+// Everything after the streaming pass, for one group: NW warps take part in the reductions
+// (NT = 32 NW threads, barrier `bar`, `gt` = thread index in the group) of which the first NC
+// threads are the consumers that streamed the map (NC == NT in the persistent kernel; the
+// cluster kernel's producer warp joins the reductions with neutral values, NT = NC + 32).
+// Resolve the first maximal element inside the winning slice, reduce (value, index) over the group
+// and the cluster, run the soft-arg-max pass, write the outputs.
+// smax[t*NC + c] = maximum of consumer c's slice of tile t, i.e. of chunks {(t*U + u)*NC + c}.
+template <int DT, int MODE, int NW, int NC, int U>
 __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScratch& sc, const uint16_t* smax,
                                                 const uint4* mp, int64_t map, int rank, int c_begin, int n,
                                                 int n_tiles, float run_max, int run_tile, const uint4 (&run_v)[U],
@@ -215,7 +218,7 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
     const bool isn = (run_max != run_max);
 #pragma unroll
     for (int u = U - 1; u >= 0; --u) {
-      const int c = (run_tile * U + u) * NT + gt;
+      const int c = (run_tile * U + u) * NC + gt;
 #pragma unroll
       for (int j = PER - 1; j >= 0; --j) {
         const float e = E::get(run_v[u], j);
@@ -256,7 +259,7 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
   if (MODE == MVGEO_SOFT_GLOBAL) {
     const float thr = M - p.skip_delta;  // NaN peak: every comparison is false, nothing accumulates
     const uint4* sm4 = reinterpret_cast<const uint4*>(smax);
-    const int groups = n_tiles * (NT / 8);
+    const int groups = n_tiles * (NC / 8);
     for (int g = gt; g < groups; g += NT) {
       const uint4 cv = sm4[g];  // 8 slice maxima
       if (CE::chunk_max(cv) >= thr) {
@@ -264,10 +267,10 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
         for (int j = 0; j < 8; ++j) {
           if (CE::get(cv, j) >= thr) {
             const int e = g * 8 + j;
-            const int t = e / NT, owner = e - t * NT;
+            const int t = e / NC, owner = e - t * NC;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const int c = (t * U + u) * NT + owner;
+              const int c = (t * U + u) * NC + owner;
               if (c < n) {
                 const uint4 ch = ld_stream(seg + c);
                 const int flat0 = (c_begin + c) * PER;
@@ -434,10 +437,10 @@ __global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const Deco
       }
     }
     if (PERSIST)
-      decode_epilogue<DT, MODE, NW, U>(p, sc[g], smax, mp, map, rank, c_begin, n, n_tiles, run_max, run_tile, run_v,
+      decode_epilogue<DT, MODE, NW, NT, U>(p, sc[g], smax, mp, map, rank, c_begin, n, n_tiles, run_max, run_tile, run_v,
                                        1 + g, gt);
     else
-      decode_epilogue<DT, MODE, kDecWarps + 1, U>(p, sc[0], smax, mp, map, rank, c_begin, n, n_tiles, run_max,
+      decode_epilogue<DT, MODE, kDecWarps + 1, NT, U>(p, sc[0], smax, mp, map, rank, c_begin, n, n_tiles, run_max,
                                                   run_tile, run_v, 0, gt);
   }
 }

@@ -752,3 +752,65 @@ def test_graphed_pipeline_matches_eager_and_reports_latency(mv):
     us = e0.elapsed_time(e1) / 50 * 1e3
     print(f"graphed C1 pipeline: {us:.1f} us per 8-frame batch")
     assert us < 200.0
+
+
+def test_other_kernels_write_only_their_outputs(mv):
+    """Canaries around every output of the encoder, MSE gradient, FK, projection, DLT and PnP kernels."""
+    import ctypes as C
+    lib = mv._lib.load()
+    rng = np.random.default_rng(3)
+    st = torch.cuda.current_stream().cuda_stream
+    CAN = 96
+
+    def guarded(n, dt=torch.float32):
+        t = torch.full((CAN + n + CAN,), -777, dtype=dt, device=DEV)
+        return t, t.data_ptr() + CAN * t.element_size()
+
+    def intact(t, n):
+        return bool((t[:CAN] == -777).all() and (t[CAN + n:] == -777).all() and not (t[CAN:CAN + n] == -777).all())
+
+    chain = mv.Chain.builtin("fr5")
+    V, B, K, J = 3, 37, chain.n_points, chain.n_joints
+    rig = mv.CameraRig.synthetic_ring_for("fr5", V, distortion=True)
+    cams = mv.ops.cameras_to_device(rig, DEV)
+    Rv = torch.from_numpy(np.stack([np.asarray(mv.view_rotation("fr5", v)) for v in ("top", "left", "right")]).astype(np.float32)).to(DEV)
+    q = torch.from_numpy(rng.uniform(-100, 100, (B, J)).astype(np.float32)).to(DEV)
+    X, pX = guarded(B * V * K * 3)
+    assert lib.mvgeo_fk(C.byref(chain.struct), q.data_ptr(), B, Rv.data_ptr(), V, pX, st) == 0
+    uv, puv = guarded(B * V * K * 2)
+    assert lib.mvgeo_project(pX, 1, cams.data_ptr(), B, V, K, puv, st) == 0
+    X2, pX2 = guarded(B * V * K * 3)
+    uv2, puv2 = guarded(B * V * K * 2)
+    fl, pfl = guarded(B)
+    ls, pls = guarded(1)
+    assert lib.mvgeo_fk_reproj_fwd(C.byref(chain.struct), q.data_ptr(), B, Rv.data_ptr(), cams.data_ptr(), V, puv, None, 1.0,
+                                   pX2, puv2, pfl, pls, st) == 0
+    dq, pdq = guarded(B * J)
+    gt = (uv[CAN:CAN + B * V * K * 2] + 3.0).contiguous()
+    assert lib.mvgeo_fk_reproj_bwd(C.byref(chain.struct), q.data_ptr(), B, Rv.data_ptr(), cams.data_ptr(), V, gt.data_ptr(), None,
+                                   1.0, None, pdq, st) == 0
+    P = torch.from_numpy(rig.projection_matrices(Rv.cpu().numpy().astype(np.float64))).to(DEV)
+    Xt, pXt = guarded(B * K * 3)
+    rs, prs = guarded(B * K)
+    nv, pnv = guarded(B * K, torch.int32)
+    assert lib.mvgeo_triangulate(puv, None, P.data_ptr(), B, V, K, 0.0, 0, pXt, prs, pnv, st) == 0
+    rv, prv = guarded(B * V * 3)
+    tv, ptv = guarded(B * V * 3)
+    rm, prm = guarded(B * V)
+    sts, psts = guarded(B * V, torch.int32)
+    assert lib.mvgeo_pnp_refine(pX, 1, gt.data_ptr(), None, cams.data_ptr(), B, V, K, 0.0, 10, prv, ptv, prm, psts, st) == 0
+    for H, W, dt, DT in ((24, 40, torch.bfloat16, 1), (9, 11, torch.float32, 0), (128, 128, torch.float32, 0)):
+        n = 5
+        kp = torch.from_numpy(np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1).astype(np.float32)).to(DEV)
+        m, pm = guarded(n * H * W, dt)
+        assert lib.mvgeo_encode_gaussian(kp.data_ptr(), n, H, W, 2.0, DT, pm, st) == 0
+        g_, pg = guarded(n * H * W, dt)
+        part, ppart = guarded(n)
+        l1, pl1 = guarded(1)
+        assert lib.mvgeo_heatmap_mse(pm, DT, kp.data_ptr(), n, H, W, 2.5, 10.0, ppart, pl1, pg, st) == 0
+        torch.cuda.synchronize()
+        assert intact(m, n * H * W) and intact(g_, n * H * W) and intact(part, n) and intact(l1, 1), (H, W, dt)
+    torch.cuda.synchronize()
+    for t, n in ((X, B * V * K * 3), (uv, B * V * K * 2), (X2, B * V * K * 3), (uv2, B * V * K * 2), (fl, B), (ls, 1), (dq, B * J),
+                 (Xt, B * K * 3), (rs, B * K), (nv, B * K), (rv, B * V * 3), (tv, B * V * 3), (rm, B * V), (sts, B * V)):
+        assert intact(t, n)

@@ -322,11 +322,11 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
 
 // G independent consumer groups per CTA (8/G warps each, own ring, own mbarriers, own named
 // barrier, own map sequence): small maps use G > 1 so that one group's latency-bound epilogue
-// overlaps the other groups' streaming. Producer lane g of the 9th warp feeds group g.
+// overlaps the other groups' streaming. Producer warp 8+g (one elected lane) feeds group g.
 // PERSIST: grid = one resident wave, group (blockIdx.x, g) walks maps blockIdx.x*G + g, +gridDim.x*G, ...
 // !PERSIST (G == 1): one segment of a cluster-split map per CTA, producer warp joins the epilogue.
 template <int DT, int MODE, int U, int STAGES, int G, bool PERSIST>
-__global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const DecodeParams p) {
   static_assert(PERSIST || G == 1, "cluster-split maps use one consumer group");
   constexpr int NW = kDecWarps / G;  // consumer warps per group
   constexpr int NT = NW * 32;
@@ -356,10 +356,11 @@ __global__ void __launch_bounds__(kDecThreads + 32) decode_tma_kernel(const Deco
   }
   __syncthreads();
 
-  if (warp == kDecWarps) {
-    // ------------------------------- producers --------------------------------------------
-    if (lane < G) {
-      const int g = lane;
+  if (warp >= kDecWarps) {
+    // ------------------------------- producers: one warp per group (a lane suspended in try_wait
+    // must not stall another group's producer), lane 0 issues ------------------------------------
+    if (lane == 0) {
+      const int g = warp - kDecWarps;
       uint4* ring = reinterpret_cast<uint4*>(dyn_smem) + (size_t)g * STAGES * kTile;
       const int64_t first = PERSIST ? (int64_t)blockIdx.x * G + g : (int64_t)(blockIdx.x / S);
       int s = 0, k = 0;  // slot, and how many times the ring has wrapped
@@ -528,11 +529,11 @@ static int launch_persistent(const DecodeParams& p, size_t smem, cudaStream_t st
   int dev = 0, sms = 0, per_sm = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
   MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32, smem));
+  MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, smem));
   if (per_sm < 1) return MVGEO_EUNSUPPORTED;
   const int64_t resident = (int64_t)sms * per_sm;
   const int64_t wanted = (p.n_maps + G - 1) / G;
-  return launch_clustered(kern, p, (unsigned)(wanted < resident ? wanted : resident), kDecThreads + 32, smem, st);
+  return launch_clustered(kern, p, (unsigned)(wanted < resident ? wanted : resident), kDecThreads + 32 * G, smem, st);
 }
 
 template <int DT, int MODE>

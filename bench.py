@@ -82,6 +82,18 @@ def _intrinsics():
     return [[[v[0], 0.0, v[2]], [0.0, v[1], v[3]], [0.0, 0.0, 1.0]] for v in mvgeo.ZEDX_FHD1200.values()]
 
 
+def _config(world: int, n_keypoints: int) -> dict:
+    """The `config` object of the JSON line (identical for both arms)."""
+    esize = 2 if MAP_DTYPE == "bf16" else 4
+    nbytes = V * n_keypoints * H * W * esize * B
+    return {"workload": WORKLOAD, "robot": ROBOT, "views": V, "keypoints": n_keypoints, "frames_per_gpu_per_step": B,
+            "map": [H, W], "map_dtype": MAP_DTYPE, "soft_argmax": f"global beta={BETA}",
+            "l2": f"inputs are {nbytes / 1e9:.2f} GB per step per GPU" +
+                  (" (>> 126 MB L2): no flush needed" if nbytes > 4e8 else " (< L2): L2 flushed by a 256 MB write between steps"),
+            "result_gather": ("results of every batch (X_tri, kp_soft, score, X_fk) kept in a device ring; ONE final nccl "
+                              "all_gather_into_tensor per job, inside the timed region") if world > 1 else "none (1 GPU)"}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
 
@@ -145,7 +157,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * B / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path; ms_per_step = time for one 1024-frame batch at the measured rate"},
+        "config": _config(1, {"fr3": 8, "fr5": 7, "meca500": 7}[ROBOT]),
+        "note": f"CPU path of the same workload; ms_per_step = time for one {B}-frame batch at the measured rate",
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,12 +346,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "robot": ROBOT, "views": V, "keypoints": K, "frames_per_gpu_per_step": B,
-                       "map": [H, W], "map_dtype": MAP_DTYPE, "soft_argmax": f"global beta={BETA}",
-                       "l2": f"inputs are {frame_bytes * B / 1e9:.2f} GB per step per GPU" +
-                             (" (>> 126 MB L2): no flush needed" if frame_bytes * B > 4e8 else
-                              " (< L2): L2 flushed by a 256 MB write between steps"),
-                       "result_gather": "results of every batch (X_tri, kp_soft, score, X_fk) kept in a device ring; ONE final nccl all_gather_into_tensor per job, inside the timed region" if world > 1 else "none (1 GPU)"},
+            "config": _config(world, K),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _profiled_traffic() if args.workload == "c2" else None, "algorithmic_bytes": frame_bytes * B,
                          "kernel": f"decode_tma_kernel<{MAP_DTYPE}, global, persistent>", "peak_source": peak_src,

@@ -814,3 +814,25 @@ def test_other_kernels_write_only_their_outputs(mv):
     for t, n in ((X, B * V * K * 3), (uv, B * V * K * 2), (X2, B * V * K * 3), (uv2, B * V * K * 2), (fl, B), (ls, 1), (dq, B * J),
                  (Xt, B * K * 3), (rs, B * K), (nv, B * K), (rv, B * V * 3), (tv, B * V * 3), (rm, B * V), (sts, B * V)):
         assert intact(t, n)
+
+
+def test_bench_line_contract():
+    """bench.py prints ONE JSON line with every key of the measurement contract (short run, no e2e / CPU legs)."""
+    import json, subprocess, sys
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--no-e2e",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "frames/s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["achieved"] > 3000 and d["value"] > 5e5 and d["gpu_launches"] == 12
+    assert abs(d["value"] - 1024 * 3 / (d["ms_per_step"] * 3e-3)) < 1e-3 * d["value"]
+    assert d["config"]["workload"].startswith("C2") and not any(x in d["clocks"]["reasons"] for x in ("hw_slowdown", "hw_thermal_slowdown"))
+    assert d["check"]["frames_with_all_views"] > 0.99 and d["check"]["rms_reproj_px"] < 3.0

@@ -229,6 +229,7 @@ def test_bench_reference_arm_contract():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["metric"] == "frames/s decode+triangulate+FK" and d["config"]["workload"].startswith("C2")
+    assert d["config"]["views"] == 4 and d["config"]["map"] == [240, 320] and d["config"]["map_dtype"] == "bf16"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0

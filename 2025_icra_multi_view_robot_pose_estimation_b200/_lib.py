@@ -69,7 +69,7 @@ _SIGNATURES = {
     "mvgeo_fk_reproj_bwd": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp], _i),
     "mvgeo_pnp_refine": ([_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_encode_gaussian": ([_vp, _i64, _i, _i, _f, _i, _vp, _vp], _i),
-    "mvgeo_heatmap_mse": ([_vp, _i, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp, _vp], _i),
+    "mvgeo_heatmap_mse": ([_vp, _i, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_pipeline": ([C.POINTER(PipelineCfg), _vp, _i64, _vp, C.POINTER(ChainStruct), _vp, _vp, _vp,
                         C.POINTER(PipelineOut), _vp], _i),
     "mvgeo_ctx_create": ([C.POINTER(_vp), _i, C.POINTER(PipelineCfg), C.POINTER(ChainStruct), _i64], _i),

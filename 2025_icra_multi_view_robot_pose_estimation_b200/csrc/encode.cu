@@ -80,6 +80,21 @@ __device__ __forceinline__ void row_values(const float* ex, int x, float vy, flo
   }
 }
 
+// Same without the eps*max cut-off: in the MSE the cut-off only replaces values < 2.2e-16 by 0,
+// which cannot change a float32 difference pred - g (the encoder keeps the cut-off: exact zeros
+// are part of create_gt_heatmap's contract).
+template <int PER>
+__device__ __forceinline__ void row_values_nocut(const float* ex, int x, float vy, float* v) {
+#pragma unroll
+  for (int q = 0; q < PER / 4; ++q) {
+    const float4 e = *reinterpret_cast<const float4*>(ex + x + 4 * q);
+    v[4 * q + 0] = e.x * vy;
+    v[4 * q + 1] = e.y * vy;
+    v[4 * q + 2] = e.z * vy;
+    v[4 * q + 3] = e.w * vy;
+  }
+}
+
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -139,10 +154,12 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const float* __rest
 template <int DT, bool VEC, bool ROW, bool GRAD>
 __global__ void __launch_bounds__(kEncThreads, 4)
     mse_kernel(const void* __restrict__ pred, const float* __restrict__ kp, int64_t n_maps, int H, int W,
-               float inv_2s2_log2e, float grad_scale, float* __restrict__ partial, void* __restrict__ grad) {
+               float inv_2s2_log2e, float grad_scale, const float* __restrict__ dloss, float* __restrict__ partial,
+               void* __restrict__ grad) {
   using E = Elem<DT>;
   extern __shared__ __align__(16) float tab[];
   __shared__ float red[kEncWarps];
+  if (GRAD && dloss) grad_scale *= dloss[0];  // upstream gradient of the scalar loss, read on the device
   float* ex = tab;
   float* ey = tab + ((W + 3) & ~3);
   const int n = H * W;
@@ -170,15 +187,14 @@ __global__ void __launch_bounds__(kEncThreads, 4)
             float g[PER], gv[PER];
             if (ROW) {
               const int y = c / cpr, x = (c - y * cpr) * PER;
-              row_values<PER>(ex, x, ey[y], thr, g);
+              row_values_nocut<PER>(ex, x, ey[y], g);
             } else {
               const int flat0 = c * PER;
               int y = flat0 / W, x = flat0 - y * W;
               float vy = ey[y];
 #pragma unroll
               for (int j = 0; j < PER; ++j) {
-                const float t = ex[x] * vy;
-                g[j] = t < thr ? 0.f : t;
+                g[j] = ex[x] * vy;
                 if (++x == W) {
                   x = 0;
                   ++y;
@@ -245,20 +261,22 @@ static int launch_encode(const float* kp, int64_t n_maps, int H, int W, float k,
 
 template <int DT, bool VEC, bool ROW>
 static void launch_mse2(const void* pred, const float* kp, int64_t n_maps, int H, int W, float k, float gs,
-                        float* partial, void* grad, unsigned g, size_t smem, cudaStream_t st) {
-  if (grad) mse_kernel<DT, VEC, ROW, true><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
-  else mse_kernel<DT, VEC, ROW, false><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, partial, grad);
+                        const float* dloss, float* partial, void* grad, unsigned g, size_t smem, cudaStream_t st) {
+  if (grad)
+    mse_kernel<DT, VEC, ROW, true><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad);
+  else
+    mse_kernel<DT, VEC, ROW, false><<<g, kEncThreads, smem, st>>>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad);
 }
 
 template <int DT>
 static int launch_mse(const void* pred, const float* kp, int64_t n_maps, int H, int W, float k, float gs,
-                      float* partial, void* grad, bool vec, cudaStream_t st) {
+                      const float* dloss, float* partial, void* grad, bool vec, cudaStream_t st) {
   const size_t smem = (size_t)(((W + 3) & ~3) + H) * sizeof(float);
   const unsigned g = maps_grid(n_maps);
   const bool row = vec && (W % Elem<DT>::kPerChunk == 0);
-  if (row) launch_mse2<DT, true, true>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
-  else if (vec) launch_mse2<DT, true, false>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
-  else launch_mse2<DT, false, false>(pred, kp, n_maps, H, W, k, gs, partial, grad, g, smem, st);
+  if (row) launch_mse2<DT, true, true>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, g, smem, st);
+  else if (vec) launch_mse2<DT, true, false>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, g, smem, st);
+  else launch_mse2<DT, false, false>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, g, smem, st);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }
@@ -292,7 +310,8 @@ extern "C" int mvgeo_encode_gaussian(const float* kp, int64_t n_maps, int H, int
 }
 
 extern "C" int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, int64_t n_maps, int H, int W,
-                                 float sigma, float weight, float* partial, float* loss, void* grad, void* stream) {
+                                 float sigma, float weight, const float* dloss, float* partial, float* loss, void* grad,
+                                 void* stream) {
   int rc = check_maps_args(n_maps, H, W, dtype, sigma);
   if (rc) return rc;
   if (n_maps == 0) return MVGEO_OK;
@@ -305,9 +324,9 @@ extern "C" int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, i
   const float gs = (float)(2.0 * (double)weight / N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
-    case MVGEO_F32: rc = launch_mse<MVGEO_F32>(pred, kp, n_maps, H, W, k, gs, partial, grad, vec, st); break;
-    case MVGEO_BF16: rc = launch_mse<MVGEO_BF16>(pred, kp, n_maps, H, W, k, gs, partial, grad, vec, st); break;
-    default: rc = launch_mse<MVGEO_F16>(pred, kp, n_maps, H, W, k, gs, partial, grad, vec, st); break;
+    case MVGEO_F32: rc = launch_mse<MVGEO_F32>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, vec, st); break;
+    case MVGEO_BF16: rc = launch_mse<MVGEO_BF16>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, vec, st); break;
+    default: rc = launch_mse<MVGEO_F16>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, vec, st); break;
   }
   if (rc) return rc;
   rc = launch_sum(partial, n_maps, loss, st);

@@ -332,26 +332,35 @@ def encode_gaussian(kp: torch.Tensor, heatmap_size, sigma: float, dtype=torch.fl
 
 
 class _HeatmapMSE(torch.autograd.Function):
+    """Forward reads the maps once (loss only); backward reads them again and writes
+    upstream * d loss / d pred in the same kernel — no materialised targets, no extra scaling pass."""
+
     @staticmethod
-    def forward(ctx, pred, kp, sigma, weight):
+    def _call(pred, kp, sigma, weight, dloss, grad):
         lib = _lib.load()
         dev = pred.device
         H, W = int(pred.shape[-2]), int(pred.shape[-1])
         n_maps = pred.numel() // (H * W)
         partial = torch.empty((n_maps,), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        grad = torch.empty_like(pred) if pred.requires_grad else None
         with torch.cuda.device(dev):
             _lib.check(lib.mvgeo_heatmap_mse(pred.data_ptr(), _DTYPES[pred.dtype], kp.data_ptr(), n_maps, H, W,
-                                             float(sigma), float(weight), partial.data_ptr(), loss.data_ptr(),
-                                             _ptr(grad), _stream(dev)), "mvgeo_heatmap_mse")
-        ctx.save_for_backward(grad)
+                                             float(sigma), float(weight), _ptr(dloss), partial.data_ptr(),
+                                             loss.data_ptr(), _ptr(grad), _stream(dev)), "mvgeo_heatmap_mse")
         return loss
 
     @staticmethod
+    def forward(ctx, pred, kp, sigma, weight):
+        ctx.save_for_backward(pred, kp)
+        ctx.sigma, ctx.weight = float(sigma), float(weight)
+        return _HeatmapMSE._call(pred, kp, sigma, weight, None, None)
+
+    @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return (grad * g.to(grad.dtype) if grad is not None else None), None, None, None
+        pred, kp = ctx.saved_tensors
+        grad = torch.empty_like(pred)
+        _HeatmapMSE._call(pred, kp, ctx.sigma, ctx.weight, g.to(dtype=torch.float32).contiguous(), grad)
+        return grad, None, None, None
 
 
 def heatmap_mse_loss(pred: torch.Tensor, kp: torch.Tensor, sigma: float, weight: float = 1.0) -> torch.Tensor:

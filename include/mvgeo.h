@@ -238,10 +238,12 @@ int mvgeo_encode_gaussian(const float* kp, int64_t n_maps, int H, int W, float s
 /* ------------------------------------------ heat-map MSE loss, fwd / bwd
  * nn.MSELoss()(pred, gt) * weight (model/MvRoPose_FR3.py:846-847,975) with the target
  * generated on the fly from key-point centres (no materialised GT maps):
- *   partial [n_maps] f32 scratch, loss [1] f32, grad [n_maps,H,W] of `dtype` (nullable)
+ *   partial [n_maps] f32 scratch, loss [1] f32,
+ *   grad [n_maps,H,W] of `dtype` (nullable) = dloss * d loss / d pred, dloss [1] f32 device scalar
+ *   (the upstream gradient; nullable = 1), so autograd needs no extra pass to scale the gradient.
  */
 int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, int64_t n_maps, int H, int W,
-                      float sigma, float weight, float* partial, float* loss, void* grad,
+                      float sigma, float weight, const float* dloss, float* partial, float* loss, void* grad,
                       void* stream);
 
 /* -------------------------------------------------------- fused pipeline

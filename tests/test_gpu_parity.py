@@ -807,7 +807,7 @@ def test_other_kernels_write_only_their_outputs(mv):
         g_, pg = guarded(n * H * W, dt)
         part, ppart = guarded(n)
         l1, pl1 = guarded(1)
-        assert lib.mvgeo_heatmap_mse(pm, DT, kp.data_ptr(), n, H, W, 2.5, 10.0, ppart, pl1, pg, st) == 0
+        assert lib.mvgeo_heatmap_mse(pm, DT, kp.data_ptr(), n, H, W, 2.5, 10.0, None, ppart, pl1, pg, st) == 0
         torch.cuda.synchronize()
         assert intact(m, n * H * W) and intact(g_, n * H * W) and intact(part, n) and intact(l1, 1), (H, W, dt)
     torch.cuda.synchronize()

@@ -26,8 +26,8 @@ def t(fn, n=20):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return statistics.median(ts)
 enc = lambda: lib.mvgeo_encode_gaussian(kp.data_ptr(), n_maps, H, W, 3.0, DT, maps.data_ptr(), st)
-fwd = lambda: lib.mvgeo_heatmap_mse(maps.data_ptr(), DT, kp.data_ptr(), n_maps, H, W, 3.0, 100.0, partial.data_ptr(), loss.data_ptr(), None, st)
-bwd = lambda: lib.mvgeo_heatmap_mse(maps.data_ptr(), DT, kp.data_ptr(), n_maps, H, W, 3.0, 100.0, partial.data_ptr(), loss.data_ptr(), grad.data_ptr(), st)
+fwd = lambda: lib.mvgeo_heatmap_mse(maps.data_ptr(), DT, kp.data_ptr(), n_maps, H, W, 3.0, 100.0, None, partial.data_ptr(), loss.data_ptr(), None, st)
+bwd = lambda: lib.mvgeo_heatmap_mse(maps.data_ptr(), DT, kp.data_ptr(), n_maps, H, W, 3.0, 100.0, None, partial.data_ptr(), loss.data_ptr(), grad.data_ptr(), st)
 te, tf, tb = t(enc), t(fwd), t(bwd)
 print(f"{B}x{V}x{K}x{H}x{W} {a[5] if len(a)>5 else 'bf16'}: encode {te*1e3:7.1f} us {nbytes/te/1e6:7.1f} GB/s (write) | mse fwd {tf*1e3:7.1f} us {nbytes/tf/1e6:7.1f} GB/s (read)"
       f" | mse fwd+bwd {tb*1e3:7.1f} us {2*nbytes/tb/1e6:7.1f} GB/s (read+write)  loss={float(loss):.4g}")

@@ -7,17 +7,20 @@
 // Roofline: HBM. Every map byte is read from DRAM exactly once (algorithmic bytes per map =
 // H*W*sizeof(dtype); outputs are 28 B per map). Design:
 //   * PERSISTENT kernel: (SMs x resident CTAs) CTAs, each walking maps blockIdx.x, +gridDim.x, ...
-//     One producer lane per CTA issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of 8 KB
+//     One elected producer lane per map stream issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of 8 KB
 //     tiles into a 4-stage shared-memory ring with full/empty mbarriers; 8 consumer warps read
 //     the tiles with conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by
 //     registers, and the producer keeps prefetching the NEXT map while the consumers are in the
 //     latency-bound per-map epilogue (consumer-only named barrier), so the DRAM pipe never drains;
 //   * pass 1 does the minimum ALU work per byte: a packed max.NaN tree per 16-byte chunk
-//     (bf16x2 / f16x2 SIMD for 16-bit maps), one (max, first-chunk) update per chunk, and (global
-//     soft mode only) one 2-byte st.shared per thread per tile of the tile-slice maximum;
-//   * the arg-max index is resolved afterwards by re-reading ONE chunk per thread, then a
-//     warp-shuffle / shared-memory (/ DSMEM) (value, index) reduction with torch.argmax's
-//     first-maximum, NaN-is-maximal ordering;
+//     (bf16x2 / f16x2 SIMD for 16-bit maps), ONE running-maximum update per thread per tile
+//     (a "slice" = the 2 chunks a thread owns in a tile), and (global soft mode only) one 2-byte
+//     st.shared of the slice maximum;
+//   * the raw chunks of the best slice stay in registers, so the first maximal element is
+//     resolved without touching memory again; then a warp-shuffle / shared-memory (/ DSMEM)
+//     (value, index) reduction with torch.argmax's first-maximum, NaN-is-maximal ordering;
+//   * maps up to 112 KB run 4 independent map streams per CTA (consumer groups of 2 warps, each
+//     with its own ring, mbarriers, named barrier and producer warp) so that epilogues overlap;
 //   * pass 2 (soft-arg-max) is exact with respect to the TRUE map maximum: threads scan the
 //     slice maxima in shared memory, 8 per ld.shared.v4, and re-read from L2 only slices that can
 //     carry a weight >= exp(-32) (a handful per peaked map), so there is no online-softmax
@@ -26,6 +29,8 @@
 //   * maps whose slice-maxima table cannot fit one CTA (> ~2.4 MB) are split over a thread-block
 //     cluster of <= 8 CTAs and combined through distributed shared memory.
 #include <cooperative_groups.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -525,15 +530,37 @@ static int launch_clustered(K kern, const DecodeParams& p, unsigned grid, int th
 template <int DT, int MODE, int G>
 static int launch_persistent(const DecodeParams& p, size_t smem, cudaStream_t st) {
   auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G, true>;
-  if (smem > 40 * 1024) MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0, per_sm = 0;
+  // Resident-wave size for this (instantiation, shared-memory size, device): a pure function of
+  // its key, cached because the occupancy query costs microseconds on a latency-bound call.
+  // (Benign cache, not state: a racing thread recomputes the same value.)
+  static std::atomic<uint64_t> cache{0};  // [63:48] device+1, [47:16] smem, [15:0] resident CTAs / SM count packed below
+  int dev = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
-  MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, smem));
-  if (per_sm < 1) return MVGEO_EUNSUPPORTED;
-  const int64_t resident = (int64_t)sms * per_sm;
+  const uint64_t key = ((uint64_t)(dev + 1) << 48) | ((uint64_t)(smem & 0xffffffffu) << 16);
+  uint64_t c = cache.load(std::memory_order_relaxed);
+  int resident_ctas;
+  if ((c & ~0xffffull) == key) {
+    resident_ctas = (int)(c & 0xffff);
+  } else {
+    if (smem > 40 * 1024)
+      MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 0;
+    MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, smem));
+    if (per_sm < 1) return MVGEO_EUNSUPPORTED;
+    resident_ctas = sms * per_sm;
+    if (resident_ctas > 0xffff) resident_ctas = 0xffff;
+    cache.store(key | (uint64_t)resident_ctas, std::memory_order_relaxed);
+  }
   const int64_t wanted = (p.n_maps + G - 1) / G;
-  return launch_clustered(kern, p, (unsigned)(wanted < resident ? wanted : resident), kDecThreads + 32 * G, smem, st);
+  const unsigned grid = (unsigned)(wanted < resident_ctas ? wanted : resident_ctas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kDecThreads + 32 * G, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  MVGEO_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  return MVGEO_OK;
 }
 
 template <int DT, int MODE>
@@ -613,11 +640,12 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
   if (vec) {
     // Work decomposition is a function of the map size only (never of n_maps), so results are
     // bit-identical however the frames are sharded across GPUs:
-    //   small maps  -> several consumer groups per CTA, one map stream each (epilogues overlap);
+    //   small maps  -> several consumer groups per CTA, one map stream each (epilogues overlap):
+    //                  4 up to 112 KB (native 128x128 fp32, C1), 2 up to 160 KB (C2 / C3), measured;
     //   large maps  -> one group; split over a cluster only when the slice-maxima table
     //                  (2 bytes per kTmaU chunks) cannot fit one CTA.
     const int64_t chunks = map_bytes / 16;
-    groups = map_bytes <= 112 * 1024 ? 4 : 1;
+    groups = map_bytes <= 112 * 1024 ? 4 : (map_bytes <= 160 * 1024 ? 2 : 1);
     const int64_t tile = (int64_t)(kDecThreads / groups) * kTmaU;
     int splits = 1;
     while (splits < kMaxSplits && ((chunks + splits - 1) / splits + tile - 1) / tile * kDecThreads * 2 > kMaxTableBytes)

@@ -9,7 +9,7 @@
 // (model/MV-model.ipynb:942-950). The reference has no backward; the gradient here is analytic.
 //
 // Roofline: FP32 latency. ~0.6 kFLOP + J sincos per frame for the chain and ~40 FLOP per
-// projected point; bytes are < 1 KB per frame. One thread owns one frame: the chain is a serial
+// projected point; bytes are < 1 KB per frame. One thread owns one (frame, view): the chain is a serial
 // product of J 3x4 transforms held in registers, the J joint axes needed by the backward are
 // kept alongside, and per-frame results are written without atomics (deterministic).
 //

@@ -262,36 +262,51 @@ __device__ __forceinline__ void decode_epilogue(const DecodeParams& p, BlockScra
 
   float s = 0.f, sx = 0.f, sy = 0.f;
   if (MODE == MVGEO_SOFT_GLOBAL) {
+    // Scan: every thread tests 8 slice maxima per 16-byte shared-memory load. Gather: a group
+    // with passing slices is broadcast through the warp (ballot + shuffle) and its up-to 8*U
+    // chunks are taken by 8*U different lanes, so all candidate re-reads are in flight together
+    // instead of one thread walking them load-by-load. Lane-to-chunk assignment and the reduction
+    // order are fixed: deterministic.
+    static_assert(8 * U <= 32, "one warp pass per group of 8 slices");
     const float thr = M - p.skip_delta;  // NaN peak: every comparison is false, nothing accumulates
     const uint4* sm4 = reinterpret_cast<const uint4*>(smax);
     const int groups = n_tiles * (NC / 8);
-    for (int g = gt; g < groups; g += NT) {
-      const uint4 cv = sm4[g];  // 8 slice maxima
-      if (CE::chunk_max(cv) >= thr) {
+    const int lane = gt & 31;
+    for (int g0 = 0; g0 < groups; g0 += NT) {  // warp-uniform trip count
+      const int g = g0 + gt;
+      unsigned m8 = 0;
+      if (g < groups) {
+        const uint4 cv = sm4[g];  // 8 slice maxima
+        if (CE::chunk_max(cv) >= thr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (CE::get(cv, j) >= thr) {
-            const int e = g * 8 + j;
-            const int t = e / NC, owner = e - t * NC;
+          for (int j = 0; j < 8; ++j) m8 |= (CE::get(cv, j) >= thr) ? (1u << j) : 0u;
+        }
+      }
+      unsigned ball = __ballot_sync(0xffffffffu, m8 != 0);
+      while (ball) {
+        const int src = __ffs(ball) - 1;
+        ball &= ball - 1;
+        const unsigned sm8 = __shfl_sync(0xffffffffu, m8, src);
+        const int sg = __shfl_sync(0xffffffffu, g, src);
+        const int j = lane / U, u = lane - j * U;
+        if (lane < 8 * U && ((sm8 >> j) & 1u)) {
+          const int e = sg * 8 + j;
+          const int t = e / NC, owner = e - t * NC;
+          const int c = (t * U + u) * NC + owner;
+          if (c < n) {
+            const uint4 ch = ld_stream(seg + c);
+            const int flat0 = (c_begin + c) * PER;
+            int y = flat0 / p.W, x = flat0 - y * p.W;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int c = (t * U + u) * NC + owner;
-              if (c < n) {
-                const uint4 ch = ld_stream(seg + c);
-                const int flat0 = (c_begin + c) * PER;
-                int y = flat0 / p.W, x = flat0 - y * p.W;
-#pragma unroll
-                for (int e_ = 0; e_ < PER; ++e_) {
-                  const float el = E::get(ch, e_);
-                  const float w = ex2_approx((el - M) * p.beta_log2e);
-                  s += w;
-                  sx += w * (float)(x - px);
-                  sy += w * (float)(y - py);
-                  if (++x == p.W) {
-                    x = 0;
-                    ++y;
-                  }
-                }
+            for (int e_ = 0; e_ < PER; ++e_) {
+              const float el = E::get(ch, e_);
+              const float w = ex2_approx((el - M) * p.beta_log2e);
+              s += w;
+              sx += w * (float)(x - px);
+              sy += w * (float)(y - py);
+              if (++x == p.W) {
+                x = 0;
+                ++y;
               }
             }
           }

@@ -50,7 +50,7 @@ class PipelineCfg(C.Structure):
 class PipelineOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "idx", "peak", "score", "kp_hard", "kp_soft", "X_tri", "tri_resid", "tri_views", "X_fk", "uv_fk",
-        "frame_loss", "loss")]
+        "frame_loss", "loss", "ticket")]
 
 
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -67,6 +67,8 @@ _SIGNATURES = {
     "mvgeo_undistort_points": ([_vp, _vp, _i64, _i, _i, _i, _vp, _vp], _i),
     "mvgeo_fk_reproj_fwd": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_fk_reproj_bwd": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp], _i),
+    "mvgeo_geometry": ([_vp, _vp, _vp, C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp,
+                        _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_pnp_refine": ([_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_encode_gaussian": ([_vp, _i64, _i, _i, _f, _i, _vp, _vp], _i),
     "mvgeo_heatmap_mse": ([_vp, _i, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),

@@ -46,6 +46,10 @@ extern "C" int mvgeo_pipeline(const mvgeo_pipeline_cfg* cfg, const void* maps, i
                     cfg->window_radius, cfg->apply_sigmoid, 1, 1, 0, out->idx, out->peak, out->score, out->kp_hard,
                     out->kp_soft, stream);
   if (rc) return rc;
+  if (out->ticket && out->frame_loss)  // geometry tail in one launch
+    return mvgeo_geometry(kp_tri, out->score, P, chain, q, B, R_view, cams, cfg->V, cfg->K, cfg->min_score,
+                          cfg->tri_weighted, cfg->lambda, out->X_tri, out->tri_resid, out->tri_views, out->X_fk,
+                          out->uv_fk, out->frame_loss, out->loss, out->ticket, stream);
   rc = mvgeo_triangulate(kp_tri, out->score, P, B, cfg->V, cfg->K, cfg->min_score, cfg->tri_weighted, out->X_tri,
                          out->tri_resid, out->tri_views, stream);
   if (rc) return rc;
@@ -167,6 +171,7 @@ extern "C" int mvgeo_pipeline_host(mvgeo_ctx* c, const void* maps_host, int64_t 
     MVGEO_CUDA(cudaMemcpyAsync(s.q, q_host + f0 * J, sizeof(float) * n * J, cudaMemcpyHostToDevice, s.stream));
     mvgeo_pipeline_out o = s.out;
     o.loss = nullptr;
+    o.ticket = nullptr;
     if (!oh->kp_soft && !(cfg.soft_mode != MVGEO_SOFT_NONE && cfg.tri_use_soft)) o.kp_soft = nullptr;
     cfg.lambda = c->cfg.lambda * (float)((double)n / (double)B);
     int rc = mvgeo_pipeline(&cfg, s.maps, n, c->P, &c->chain, s.q, R_view_host ? c->R_view : nullptr, c->cams, &o,

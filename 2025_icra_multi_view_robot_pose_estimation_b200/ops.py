@@ -397,13 +397,16 @@ _OUT_SPECS = (  # name, dtype, shape builder (B, V, K)
     ("uv_fk", torch.float32, lambda B, V, K: (B, V, K, 2)),
     ("frame_loss", torch.float32, lambda B, V, K: (B,)),
     ("loss", torch.float32, lambda B, V, K: ()),
+    ("ticket", torch.int32, lambda B, V, K: (1,)),  # zero on entry / exit: geometry tail in one launch
 )
 
 
 def alloc_outputs(B: int, V: int, K: int, device, pin: bool = False) -> dict:
     if pin:
-        return {n: torch.empty(f(B, V, K), dtype=dt).pin_memory() for n, dt, f in _OUT_SPECS}
-    return {n: torch.empty(f(B, V, K), dtype=dt, device=device) for n, dt, f in _OUT_SPECS}
+        return {n: torch.zeros(f(B, V, K), dtype=dt).pin_memory() for n, dt, f in _OUT_SPECS}
+    out = {n: torch.empty(f(B, V, K), dtype=dt, device=device) for n, dt, f in _OUT_SPECS}
+    out["ticket"].zero_()
+    return out
 
 
 def _out_struct(out: dict) -> _lib.PipelineOut:

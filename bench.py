@@ -233,8 +233,8 @@ def run_ours(args):
     import ctypes as C
 
     def step():
-        """decode -> triangulate -> FK + reprojection consistency through the C ABI (the same three
-        launches mvgeo_pipeline makes), with CUDA events around the decode kernel."""
+        """decode -> (triangulate || FK + reprojection consistency + loss sum) through the C ABI: the same
+        two launches mvgeo_pipeline makes, with CUDA events around the decode kernel."""
         j = counter[0] % n_slots
         if world > 1 and counter[0] > 0 and j == 0:
             ring.final_gather()  # ring full (more than 128 batches in the job): flush before re-use
@@ -252,11 +252,11 @@ def run_ours(args):
                               1, 1, 0, out["idx"].data_ptr(), out["peak"].data_ptr(), out["score"].data_ptr(),
                               out["kp_hard"].data_ptr(), out["kp_soft"].data_ptr(), s)
         e1.record(st)
-        rc |= lib.mvgeo_triangulate(out["kp_soft"].data_ptr(), out["score"].data_ptr(), P.data_ptr(), B, V, K, MIN_SCORE, 0,
-                                    out["X_tri"].data_ptr(), out["tri_resid"].data_ptr(), out["tri_views"].data_ptr(), s)
-        rc |= lib.mvgeo_fk_reproj_fwd(C.byref(chain.struct), q.data_ptr(), B, Rvt.data_ptr(), cams.data_ptr(), V,
-                                      out["kp_soft"].data_ptr(), None, 1.0, out["X_fk"].data_ptr(), out["uv_fk"].data_ptr(),
-                                      out["frame_loss"].data_ptr(), out["loss"].data_ptr(), s)
+        rc |= lib.mvgeo_geometry(out["kp_soft"].data_ptr(), out["score"].data_ptr(), P.data_ptr(), C.byref(chain.struct),
+                                 q.data_ptr(), B, Rvt.data_ptr(), cams.data_ptr(), V, K, MIN_SCORE, 0, 1.0,
+                                 out["X_tri"].data_ptr(), out["tri_resid"].data_ptr(), out["tri_views"].data_ptr(),
+                                 out["X_fk"].data_ptr(), out["uv_fk"].data_ptr(), out["frame_loss"].data_ptr(),
+                                 out["loss"].data_ptr(), out["ticket"].data_ptr(), s)
         assert rc == 0, rc
         e2 = torch.cuda.Event(enable_timing=True)
         e2.record(st)
@@ -354,7 +354,7 @@ def run_ours(args):
                          "frac_of_nominal_8TBps": achieved / 8000.0, "bytes_per_frame": frame_bytes},
             "e2e": {"value": (B * world * e2e_steps / e2e_s) if e2e_steps else None, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "mvgeo_pipeline_host (pinned host buffers)"},
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": 2 * args.steps,
             "breakdown": {"final_gather_ms": gather_ms, "host_enqueue_ms_per_step": cpu_issue_ms,
                           "result_bytes_per_step_per_gpu": 4 * ring.record},
             "clocks": clocks,

@@ -209,6 +209,19 @@ int mvgeo_fk_reproj_bwd(const mvgeo_chain* chain, const float* q, int64_t B,
                         const float* gt_uv, const float* w, float lambda,
                         const float* dloss, float* dq, void* stream);
 
+/* ------------------------------------------------------------- geometry tail, one launch
+ * mvgeo_triangulate + mvgeo_fk_reproj_fwd (+ the loss sum) in ONE kernel: the two stages are
+ * independent (both consume the decoded key-points `kp`, which is also the consistency target, unweighted),
+ * so their CTAs share a grid; the last FK CTA (atomic ticket) sums frame_loss in a fixed order.
+ * Arguments as in the two stand-alone calls. `ticket` [1] i32 must be 0 on entry and is 0 again on
+ * exit (allocate once, zero once); required when `loss` is given.
+ */
+int mvgeo_geometry(const float* kp, const float* w, const float* P, const mvgeo_chain* chain,
+                   const float* q, int64_t B, const float* R_view, const mvgeo_camera* cams, int V, int K,
+                   float min_weight, int weighted, float lambda,
+                   float* X_tri, float* resid, int32_t* n_views, float* X_fk, float* uv_fk,
+                   float* frame_loss, float* loss, int32_t* ticket, void* stream);
+
 /* -------------------------------------------------- camera-pose refinement (PnP)
  * The step after the hot path in the reference: estimate_camera_pose
  * (model/Fr5_model_train.ipynb:4707-4753): FK points + decoded key-points with score >= threshold
@@ -247,7 +260,8 @@ int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, int64_t n_ma
                       void* stream);
 
 /* -------------------------------------------------------- fused pipeline
- * decode -> triangulate -> FK -> reprojection consistency, one stream, no host sync.
+ * decode -> triangulate -> FK -> reprojection consistency, one stream, no host sync: two launches
+ * (decode, geometry) when out->ticket is given, four otherwise.
  * Device-resident inputs. Any output pointer may be NULL except those a later stage
  * needs (kp_hard, kp_soft when soft_mode != NONE, score, X_tri).
  */
@@ -273,6 +287,8 @@ typedef struct mvgeo_pipeline_out {
   float* uv_fk;      /* [B,V,K,2] */
   float* frame_loss; /* [B]       */
   float* loss;       /* [1]       */
+  int32_t* ticket;   /* [1] zero on entry (and again on exit): lets the geometry tail run as ONE launch;
+                        NULL = separate triangulate / FK / sum launches */
 } mvgeo_pipeline_out;
 
 int mvgeo_pipeline(const mvgeo_pipeline_cfg* cfg, const void* maps, int64_t B,

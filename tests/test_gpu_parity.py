@@ -832,7 +832,45 @@ def test_bench_line_contract():
     assert d["unit"] == "frames/s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["achieved"] > 3000 and d["value"] > 5e5 and d["gpu_launches"] == 12
+    assert r["achieved"] > 3000 and d["value"] > 5e5 and d["gpu_launches"] == 6
     assert abs(d["value"] - 1024 * 3 / (d["ms_per_step"] * 3e-3)) < 1e-3 * d["value"]
     assert d["config"]["workload"].startswith("C2") and not any(x in d["clocks"]["reasons"] for x in ("hw_slowdown", "hw_thermal_slowdown"))
     assert d["check"]["frames_with_all_views"] > 0.99 and d["check"]["rms_reproj_px"] < 3.0
+
+
+@pytest.mark.parametrize("robot,V", [("fr3", 4), ("fr5", 3), ("meca500", 2)])
+def test_geometry_one_launch_equals_separate_stages(mv, robot, V):
+    """mvgeo_geometry (DLT || FK + consistency + loss sum in one kernel) == mvgeo_triangulate + mvgeo_fk_reproj_fwd."""
+    import ctypes as C
+    lib = mv._lib.load()
+    B, H, W = 77, 48, 64
+    chain, rig, Rv, q, X, uv, maps, P = _closed_loop_inputs(mv, robot, V, B, H, W, torch.float32, seed=11)
+    K = chain.n_points
+    dec = mv.decode_heatmaps(maps, rig.image_size, soft="window", beta=20.0, window_radius=4)
+    kp, score = dec.kp_soft.contiguous(), dec.score.contiguous()
+    kp[3, 0, 1] = float("nan")
+    cams = mv.ops.cameras_to_device(rig, DEV)
+    Rvt = torch.from_numpy(Rv).to(DEV)
+    Xs, rs, ns = mv.triangulate(kp, P, score, min_weight=0.3)
+    ls, Xf, uvf, fls = mv.fk_reproj_loss(chain, q, rig, kp, Rv, lam=0.5)
+    f32 = lambda *shape: torch.full(shape, -5.0, device=DEV)
+    Xt, rt, nt = f32(B, K, 3), f32(B, K), torch.full((B, K), -5, dtype=torch.int32, device=DEV)
+    Xk, uvk, flk, lk = f32(B, V, K, 3), f32(B, V, K, 2), f32(B), f32(1)
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(3):  # the ticket resets itself
+        rc = lib.mvgeo_geometry(kp.data_ptr(), score.data_ptr(), P.data_ptr(), C.byref(chain.struct), q.data_ptr(), B,
+                                Rvt.data_ptr(), cams.data_ptr(), V, K, 0.3, 0, 0.5, Xt.data_ptr(), rt.data_ptr(), nt.data_ptr(),
+                                Xk.data_ptr(), uvk.data_ptr(), flk.data_ptr(), lk.data_ptr(), ticket.data_ptr(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int(ticket) == 0
+        assert torch.equal(nt, ns) and torch.equal(torch.isnan(Xt), torch.isnan(Xs))
+        assert torch.equal(torch.nan_to_num(Xt), torch.nan_to_num(Xs)) and torch.equal(torch.nan_to_num(rt), torch.nan_to_num(rs))
+        assert torch.allclose(Xk, Xf, rtol=0, atol=1e-6) and torch.allclose(uvk, uvf, rtol=0, atol=1e-3)
+        assert torch.allclose(flk, fls, rtol=1e-5, atol=0) and abs(float(lk) - float(ls)) <= 1e-5 * abs(float(ls))
+        assert abs(float(lk) - float(flk.double().sum())) <= 1e-5 * abs(float(lk))
+        lk.fill_(-5.0)
+    assert lib.mvgeo_geometry(kp.data_ptr(), score.data_ptr(), P.data_ptr(), C.byref(chain.struct), q.data_ptr(), B, Rvt.data_ptr(),
+                              cams.data_ptr(), V, K, 0.3, 0, 0.5, Xt.data_ptr(), rt.data_ptr(), nt.data_ptr(), Xk.data_ptr(),
+                              uvk.data_ptr(), flk.data_ptr(), lk.data_ptr(), None, st) == -2   # loss without a ticket

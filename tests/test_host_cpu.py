@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(mv):
 
 def test_struct_layouts_match_header(mv):
     assert ctypes.sizeof(mv._lib.ChainStruct) == 16 + 5 * 8 * 4
-    assert ctypes.sizeof(mv._lib.PipelineOut) == 12 * 8
+    assert ctypes.sizeof(mv._lib.PipelineOut) == 13 * 8
     assert ctypes.sizeof(mv._lib.PipelineCfg) == 13 * 4 + 4 + 16  # 13 x 32-bit, pad to 8, two doubles
     assert mv.CameraRig.synthetic_ring(3).packed().shape == (3, 24)
 

@@ -37,7 +37,10 @@ __global__ void __launch_bounds__(kFkThreads)
   fk_reproj_fwd_body<BASE>(ch, q, B, R_view, cams, V, kp, nullptr, scale, X_fk, uv_fk, frame_loss, part,
                            (int64_t)blockIdx.x - n_dlt);
   if (!loss) return;
-  __threadfence();  // this CTA's frame_loss entries are visible device-wide before the ticket is taken
+  // Several warps of this CTA wrote frame_loss entries: each writer fences its own stores, the
+  // barrier makes sure EVERY writer of the CTA has done so, and only then is the ticket taken.
+  __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)(n_fk - 1));
   __syncthreads();
   if (!is_last) return;

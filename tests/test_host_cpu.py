@@ -237,3 +237,60 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                          capture_output=True, text=True, timeout=120, env=dict(env, RANK="3", WORLD_SIZE="8"), cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_header_is_plain_c_and_library_is_callable_from_c(mv, tmp_path):
+    """include/mvgeo.h compiles as C99 (no C++-isms) and a C program can dlopen the library and call the
+    host-only entry points — the boundary really is a C ABI, not a Python/C++ one."""
+    import shutil
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "mvgeo.h"
+typedef int (*version_fn)(void);
+typedef const char* (*errstr_fn)(int);
+typedef int (*chain_fn)(int, mvgeo_chain*);
+typedef int (*decode_fn)(const void*, int, int64_t, int, int, double, double, int, float, int, int, int64_t, int64_t,
+                         int64_t, int32_t*, float*, float*, float*, float*, void*);
+int main(int argc, char** argv) {
+  if (argc < 2) return 1;
+  void* h = dlopen(argv[1], RTLD_NOW);
+  if (!h) { fprintf(stderr, "%s\n", dlerror()); return 2; }
+  version_fn ver = (version_fn)dlsym(h, "mvgeo_version");
+  errstr_fn es = (errstr_fn)dlsym(h, "mvgeo_error_string");
+  chain_fn cb = (chain_fn)dlsym(h, "mvgeo_chain_builtin");
+  decode_fn dec = (decode_fn)dlsym(h, "mvgeo_decode");
+  if (!ver || !es || !cb || !dec) return 3;
+  mvgeo_chain c;
+  memset(&c, 0, sizeof c);
+  if (ver() != MVGEO_VERSION) return 4;
+  if (cb(MVGEO_ROBOT_FR3, &c) != MVGEO_OK || c.n_joints != 7 || c.convention != MVGEO_DH_MODIFIED || !c.emit_base) return 5;
+  if (cb(MVGEO_ROBOT_MECA500, &c) != MVGEO_OK || c.n_joints != 6 || c.theta_offset[1] != -90.0f) return 6;
+  if (cb(99, &c) != MVGEO_EINVAL) return 7;
+  if (dec(NULL, MVGEO_F32, 4, 8, 8, 1.0, 1.0, MVGEO_SOFT_NONE, 1.0f, 0, 0, 1, 1, 0, NULL, NULL, NULL, NULL, NULL, NULL) != MVGEO_ENULL) return 8;
+  if (dec(NULL, MVGEO_F32, 0, 8, 8, 1.0, 1.0, MVGEO_SOFT_NONE, 1.0f, 0, 0, 1, 1, 0, NULL, NULL, NULL, NULL, NULL, NULL) != MVGEO_OK) return 9;
+  printf("%d %s | sizeof(mvgeo_chain)=%zu sizeof(mvgeo_camera)=%zu sizeof(mvgeo_pipeline_out)=%zu\n", ver(), es(MVGEO_EALIGN),
+         sizeof(mvgeo_chain), sizeof(mvgeo_camera), sizeof(mvgeo_pipeline_out));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    hdr_only = tmp_path / "hdr.c"
+    hdr_only.write_text('#include "mvgeo.h"\nint mvgeo_header_ok;\n')
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I",
+                         os.path.join(ROOT, "include"), str(hdr_only)], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr  # the header itself is strictly conforming C99
+    # (the program is built without -pedantic only because ISO C has no object->function pointer cast for dlsym)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         str(src), "-o", str(exe), "-ldl"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe), mv.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.startswith("100 pointer is not aligned")
+    assert f"sizeof(mvgeo_chain)={ctypes.sizeof(mv._lib.ChainStruct)} " in run.stdout  # ctypes mirror == C layout
+    assert "sizeof(mvgeo_camera)=96 " in run.stdout and f"sizeof(mvgeo_pipeline_out)={ctypes.sizeof(mv._lib.PipelineOut)}" in run.stdout

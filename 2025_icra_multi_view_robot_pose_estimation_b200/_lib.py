@@ -60,6 +60,7 @@ _SIGNATURES = {
     "mvgeo_error_string": ([_i], C.c_char_p),
     "mvgeo_chain_builtin": ([_i, C.POINTER(ChainStruct)], _i),
     "mvgeo_decode": ([_vp, _i, _i64, _i, _i, _d, _d, _i, _f, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "mvgeo_decode_views": ([C.POINTER(_vp), _i, _i, _i64, _i, _i, _i, _d, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_triangulate": ([_vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp], _i),
     "mvgeo_quat_mean": ([_vp, _vp, _i64, _i, _vp, _vp], _i),
     "mvgeo_fk": ([C.POINTER(ChainStruct), _vp, _i64, _vp, _i, _vp, _vp], _i),
@@ -74,6 +75,8 @@ _SIGNATURES = {
     "mvgeo_heatmap_mse": ([_vp, _i, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_pipeline": ([C.POINTER(PipelineCfg), _vp, _i64, _vp, C.POINTER(ChainStruct), _vp, _vp, _vp,
                         C.POINTER(PipelineOut), _vp], _i),
+    "mvgeo_pipeline_views": ([C.POINTER(PipelineCfg), C.POINTER(_vp), _i64, _vp, C.POINTER(ChainStruct), _vp, _vp, _vp,
+                              C.POINTER(PipelineOut), _vp], _i),
     "mvgeo_ctx_create": ([C.POINTER(_vp), _i, C.POINTER(PipelineCfg), C.POINTER(ChainStruct), _i64], _i),
     "mvgeo_ctx_destroy": ([_vp], _i),
     "mvgeo_pipeline_host": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(PipelineOut)], _i),

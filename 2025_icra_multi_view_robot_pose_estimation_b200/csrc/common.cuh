@@ -61,21 +61,59 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
+// ---- packed f32x2 arithmetic (sm_100: one FFMA2 / FADD2 / FMUL2 issue slot for two lanes) ----
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+
 // ---- mbarrier + TMA bulk-copy primitives (async proxy; SASS: SYNCS.*, UBLKCP) -------------
+// Shared-memory operands are 32-bit shared-window addresses computed once (smem_u32) and then
+// advanced with integer arithmetic, so no generic->shared conversion sits in the streaming loop.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -84,15 +122,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra MVGEO_DONE_%=;\n"
       "bra MVGEO_WAIT_%=;\n"
       "MVGEO_DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
+      "}\n" ::"r"(bar),
       "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of re-polling
       : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar` (16-byte aligned, size % 16 == 0).
-__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
 }
 
@@ -134,6 +171,11 @@ template <> struct Elem<MVGEO_F32> {
   static constexpr int kBytes = 4;
   static constexpr int kPerChunk = 4;
   using carrier = float;  // how a chunk maximum is kept in shared memory
+  // elements (2i, 2i+1) of a chunk as two floats (already a register pair for f32 maps)
+  __device__ static __forceinline__ void pair(const uint4& c, int i, float& lo, float& hi) {
+    lo = __uint_as_float(i == 0 ? c.x : c.z);
+    hi = __uint_as_float(i == 0 ? c.y : c.w);
+  }
   __device__ static __forceinline__ float chunk_max(const uint4& c) {
     return max_nan_f32(max_nan_f32(__uint_as_float(c.x), __uint_as_float(c.y)),
                        max_nan_f32(__uint_as_float(c.z), __uint_as_float(c.w)));
@@ -166,6 +208,11 @@ template <> struct Elem<MVGEO_BF16> {
   static constexpr int kBytes = 2;
   static constexpr int kPerChunk = 8;
   using carrier = uint16_t;
+  __device__ static __forceinline__ void pair(const uint4& c, int i, float& lo, float& hi) {
+    const uint32_t w = i == 0 ? c.x : i == 1 ? c.y : i == 2 ? c.z : c.w;
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
   __device__ static __forceinline__ float chunk_max(const uint4& c) {
     const uint32_t m = max_nan_bf16x2(max_nan_bf16x2(c.x, c.y), max_nan_bf16x2(c.z, c.w));
     return max_nan_f32(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
@@ -202,6 +249,12 @@ template <> struct Elem<MVGEO_F16> {
   static constexpr int kPerChunk = 8;
   using carrier = uint16_t;
   __device__ static __forceinline__ float h2f(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+  __device__ static __forceinline__ void pair(const uint4& c, int i, float& lo, float& hi) {
+    const uint32_t w = i == 0 ? c.x : i == 1 ? c.y : i == 2 ? c.z : c.w;
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x;
+    hi = f.y;
+  }
   __device__ static __forceinline__ float chunk_max(const uint4& c) {
     const uint32_t m = max_nan_f16x2(max_nan_f16x2(c.x, c.y), max_nan_f16x2(c.z, c.w));
     return max_nan_f32(h2f((uint16_t)(m & 0xffffu)), h2f((uint16_t)(m >> 16)));

@@ -50,6 +50,24 @@ def _scales(image_size, H, W):
     return w_img / W, h_img / H  # Python float division, as `original_w / w` in the reference
 
 
+def _view_ptrs(views: Sequence[torch.Tensor]):
+    """Host array of V device pointers (mvgeo_decode_views / mvgeo_pipeline_views)."""
+    return (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
+
+
+def _as_view_list(maps):
+    """dict view -> (B,K,H,W) (the reference network's output, model/MvRoPose_FR3.py:625; insertion
+    order = view order), list / tuple of such tensors, or None when `maps` is one stacked tensor."""
+    if isinstance(maps, torch.Tensor):
+        return None
+    views = list(maps.values()) if isinstance(maps, dict) else list(maps)
+    views = [_need_cuda(v, "maps[view]") for v in views]
+    if not views or any(v.shape != views[0].shape or v.dtype != views[0].dtype or v.dim() != 4 or v.device != views[0].device
+                        for v in views):
+        raise ValueError("a view list must hold V tensors of identical shape (B, K, H, W), dtype and device")
+    return views
+
+
 def cameras_to_device(rig: Union[CameraRig, torch.Tensor], device) -> torch.Tensor:
     """(V,24) float32 device tensor of mvgeo_camera records."""
     if isinstance(rig, torch.Tensor):
@@ -62,9 +80,9 @@ def decode_heatmaps(maps, image_size=None, *, soft: Optional[str] = "global", be
                     window_radius: int = 3, apply_sigmoid: bool = False) -> DecodeResult:
     """Arg-max + sub-pixel soft-arg-max of belief maps.
 
-    maps: CUDA tensor (..., H, W) in fp32 / bf16 / fp16, or a sequence of V tensors (B, K, H, W)
-    (the values of the reference's dict view -> heat-maps, model/MvRoPose_FR3.py:625), in which
-    case results are (B, V, K). image_size = (H_img, W_img) scales key-points to image pixels
+    maps: CUDA tensor (..., H, W) in fp32 / bf16 / fp16, or a dict / sequence of V tensors (B, K, H, W)
+    (the reference's dict view -> heat-maps, model/MvRoPose_FR3.py:625), decoded in ONE launch
+    without a stack copy, in which case results are (B, V, K). image_size = (H_img, W_img) scales key-points to image pixels
     like extract_keypoints_from_heatmaps (model/Fr5_model_train.ipynb:4701-4702).
     Returns DecodeResult(idx int32, peak, score, kp_hard (...,2), kp_soft (...,2))."""
     lib = _lib.load()
@@ -76,9 +94,7 @@ def decode_heatmaps(maps, image_size=None, *, soft: Optional[str] = "global", be
             raise ValueError("maps must have at least 2 dimensions (H, W)")
         views, lead, strided = [t], tuple(t.shape[:-2]), False
     else:
-        views = [_need_cuda(v, "maps[view]") for v in maps]
-        if not views or any(v.shape != views[0].shape or v.dtype != views[0].dtype or v.dim() != 4 for v in views):
-            raise ValueError("a view list must hold V tensors of identical shape (B, K, H, W) and dtype")
+        views = _as_view_list(maps)
         Bv, Kv = views[0].shape[:2]
         lead, strided = (Bv, len(views), Kv), True
     t0 = views[0]
@@ -95,11 +111,14 @@ def decode_heatmaps(maps, image_size=None, *, soft: Optional[str] = "global", be
     kp_soft = torch.empty(lead + (2,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         st = _stream(dev)
-        for v, t in enumerate(views):
-            n_maps = t.numel() // (H * W)
-            k_inner, stride, off = (lead[2], lead[1] * lead[2], v * lead[2]) if strided else (1, 1, 0)
-            _lib.check(lib.mvgeo_decode(t.data_ptr(), _DTYPES[t.dtype], n_maps, H, W, sx, sy, mode, float(beta),
-                                        int(window_radius), int(bool(apply_sigmoid)), k_inner, stride, off,
+        if strided:  # V per-view tensors: ONE launch walks all of them, results land in (B, V, K) order
+            _lib.check(lib.mvgeo_decode_views(_view_ptrs(views), len(views), _DTYPES[t0.dtype], lead[0], lead[2], H, W,
+                                              sx, sy, mode, float(beta), int(window_radius), int(bool(apply_sigmoid)),
+                                              idx.data_ptr(), peak.data_ptr(), score.data_ptr(), kp_hard.data_ptr(),
+                                              kp_soft.data_ptr(), st), "mvgeo_decode_views")
+        else:
+            _lib.check(lib.mvgeo_decode(t0.data_ptr(), _DTYPES[t0.dtype], t0.numel() // (H * W), H, W, sx, sy, mode,
+                                        float(beta), int(window_radius), int(bool(apply_sigmoid)), 1, 1, 0,
                                         idx.data_ptr(), peak.data_ptr(), score.data_ptr(), kp_hard.data_ptr(),
                                         kp_soft.data_ptr(), st), "mvgeo_decode")
     assert n_out == idx.numel()
@@ -413,35 +432,50 @@ def _out_struct(out: dict) -> _lib.PipelineOut:
     return _lib.PipelineOut(*[out[n].data_ptr() if out.get(n) is not None else None for n, _, _ in _OUT_SPECS])
 
 
-def pipeline(maps: torch.Tensor, P: torch.Tensor, chain: Chain, q: torch.Tensor, cams, R_view=None, *,
+def pipeline(maps, P: torch.Tensor, chain: Chain, q: torch.Tensor, cams, R_view=None, *,
              image_size=None, soft: Optional[str] = "global", beta: float = 100.0, window_radius: int = 3,
              apply_sigmoid: bool = False, tri_use_soft: bool = True, tri_weighted: bool = False,
              min_score: float = 0.0, lam: float = 1.0, out: Optional[dict] = None) -> dict:
-    """decode -> triangulate -> FK -> reprojection consistency in three launches on the current
-    stream, no host synchronisation. maps (B,V,K,H,W); P (V,3,4); q (B,J). Returns a dict of
-    device tensors (see alloc_outputs); pass `out` to reuse buffers (e.g. under CUDA-graph capture)."""
+    """decode -> triangulate -> FK -> reprojection consistency in two launches on the current
+    stream, no host synchronisation. maps: (B,V,K,H,W), or the reference's dict view -> (B,K,H,W) /
+    a list of V such tensors (read in place through a pointer array: no torch.stack copy);
+    P (V,3,4); q (B,J). Returns a dict of device tensors (see alloc_outputs); pass `out` to reuse
+    buffers (e.g. under CUDA-graph capture)."""
     lib = _lib.load()
-    maps = _need_cuda(maps, "maps")
-    if maps.dim() != 5:
-        raise ValueError("maps must be (B, V, K, H, W)")
-    B, V, K, H, W = (int(s) for s in maps.shape)
-    dev = maps.device
+    views = _as_view_list(maps)
+    if views is None:
+        maps = _need_cuda(maps, "maps")
+        if maps.dim() != 5:
+            raise ValueError("maps must be (B, V, K, H, W)")
+        B, V, K, H, W = (int(s) for s in maps.shape)
+        dev, mdtype = maps.device, maps.dtype
+    else:
+        V = len(views)
+        B, K, H, W = (int(s) for s in views[0].shape)
+        dev, mdtype = views[0].device, views[0].dtype
+    if mdtype not in _DTYPES:
+        raise TypeError(f"unsupported belief-map dtype {mdtype}")
     P = _need_cuda(P, "P", torch.float32)
     q = _need_cuda(q, "q", torch.float32)
     if tuple(P.shape) != (V, 3, 4) or tuple(q.shape) != (B, chain.n_joints) or K != chain.n_points:
         raise ValueError("shape mismatch between maps, P, q and the chain")
     cams_t = cameras_to_device(cams, dev)
     Rv = _view_rot(R_view, dev, V)
-    cfg = _make_cfg(maps.dtype, H, W, V, K, image_size, soft, beta, window_radius, apply_sigmoid, tri_use_soft,
+    cfg = _make_cfg(mdtype, H, W, V, K, image_size, soft, beta, window_radius, apply_sigmoid, tri_use_soft,
                     tri_weighted, min_score, lam)
     if out is None:
         out = alloc_outputs(B, V, K, dev)
     o = _out_struct(out)
     with torch.cuda.device(dev):
-        _lib.check(lib.mvgeo_pipeline(C.byref(cfg), maps.data_ptr(), B, P.data_ptr(), C.byref(chain.struct),
-                                      q.data_ptr(), _ptr(Rv), cams_t.data_ptr(), C.byref(o), _stream(dev)),
-                   "mvgeo_pipeline")
-    out["_keepalive"] = (cams_t, Rv)
+        if views is None:
+            _lib.check(lib.mvgeo_pipeline(C.byref(cfg), maps.data_ptr(), B, P.data_ptr(), C.byref(chain.struct),
+                                          q.data_ptr(), _ptr(Rv), cams_t.data_ptr(), C.byref(o), _stream(dev)),
+                       "mvgeo_pipeline")
+        else:
+            _lib.check(lib.mvgeo_pipeline_views(C.byref(cfg), _view_ptrs(views), B, P.data_ptr(),
+                                                C.byref(chain.struct), q.data_ptr(), _ptr(Rv), cams_t.data_ptr(),
+                                                C.byref(o), _stream(dev)), "mvgeo_pipeline_views")
+    out["_keepalive"] = (cams_t, Rv, views)
     return out
 
 

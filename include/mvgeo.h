@@ -125,6 +125,17 @@ int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, int W,
                  int32_t* idx, float* peak, float* score, float* kp_hard, float* kp_soft,
                  void* stream);
 
+/* The same decoder over V separate per-view tensors — the reference network returns
+ * dict view -> (B,K,H,W) (model/MvRoPose_FR3.py:584-627) — in ONE launch and without a stack copy:
+ *   view_maps  HOST array of n_views DEVICE pointers, each [B, K, H, W] of `dtype` (read during the call only)
+ * Results are dense [B, n_views, K] (kp_*: [B, n_views, K, 2]); every byte of every view is read once.
+ */
+int mvgeo_decode_views(const void* const* view_maps, int n_views, int dtype, int64_t B, int K, int H, int W,
+                       double scale_x, double scale_y,
+                       int soft_mode, float beta, int window_radius, int apply_sigmoid,
+                       int32_t* idx, float* peak, float* score, float* kp_hard, float* kp_soft,
+                       void* stream);
+
 /* ---------------------------------------------------------- triangulation
  * New functionality (the reference has no triangulation).
  * Homogeneous DLT: per key-point, rows u*P[2]-P[0], v*P[2]-P[1] for every valid view,
@@ -295,6 +306,13 @@ int mvgeo_pipeline(const mvgeo_pipeline_cfg* cfg, const void* maps, int64_t B,
                    const float* P, const mvgeo_chain* chain, const float* q,
                    const float* R_view, const mvgeo_camera* cams,
                    const mvgeo_pipeline_out* out, void* stream);
+/* mvgeo_pipeline over cfg->V separate per-view tensors [B, K, H, W] (HOST array of DEVICE pointers,
+ * the values of the reference's dict of views): same two launches, same results bit for bit, no
+ * torch.stack copy of the maps. */
+int mvgeo_pipeline_views(const mvgeo_pipeline_cfg* cfg, const void* const* view_maps, int64_t B,
+                         const float* P, const mvgeo_chain* chain, const float* q,
+                         const float* R_view, const mvgeo_camera* cams,
+                         const mvgeo_pipeline_out* out, void* stream);
 
 /* Host-buffer pipeline: the call a CPU-tensor caller makes (the reference moves the maps
  * to the CPU before decoding, DIP_REAL.py:113). Inputs and outputs are HOST pointers

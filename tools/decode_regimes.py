@@ -1,0 +1,122 @@
+"""Decode-kernel throughput across DATA REGIMES (VERDICT r1 "weak #1"): global soft-arg-max over
+beta x peak amplitude x {Gaussian blob + noise, uniform noise}, per map shape, CUDA-event timed.
+Writes one JSON line per cell (algorithmic GB/s = map bytes / time) plus the soft-arg-max error against
+a float64 torch restatement on a sample of the maps.
+
+    python tools/decode_regimes.py [--lib path/to/libmvgeo.so] [--tag r02] [--shapes c2,native32,native16]
+                                   [--out gpurun_out/decode_regimes.jsonl] [--only dist:amp:beta]
+"""
+import argparse, ctypes as C, json, os, statistics, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+SHAPES = {  # name: (n_maps, H, W, dtype)
+    "c2": (1024 * 4 * 8, 240, 320, torch.bfloat16),        # BASELINE config 2: 5.03 GB
+    "native32": (2048 * 3 * 7, 128, 128, torch.float32),   # reference-native map, fp32: 2.8 GB
+    "native16": (4096 * 3 * 7, 128, 128, torch.bfloat16),  # reference-native map under bf16 autocast: 2.8 GB
+    "c5": (128 * 8 * 8, 480, 640, torch.bfloat16),         # BASELINE config 5: 5.03 GB
+}
+BETAS = (5.0, 15.0, 30.0, 100.0, 400.0)
+AMPS = (0.05, 0.3, 1.0)
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def bind(path):
+    lib = C.CDLL(path)
+    vp, i, i64, f, d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    lib.mvgeo_decode.argtypes = [vp, i, i64, i, i, d, d, i, f, i, i, i64, i64, i64, vp, vp, vp, vp, vp, vp]
+    lib.mvgeo_decode.restype = i
+    lib.mvgeo_encode_gaussian.argtypes = [vp, i64, i, i, f, i, vp, vp]
+    lib.mvgeo_encode_gaussian.restype = i
+    return lib
+
+
+def ref_soft(maps, beta):
+    """float64 soft-arg-max of (n,H,W) maps on the GPU (the specification, oracle/mvgeo_oracle.py:287-321)."""
+    n, H, W = maps.shape
+    h = maps.double().reshape(n, -1)
+    w = torch.exp(beta * (h - h.max(dim=1, keepdim=True).values))
+    s = w.sum(dim=1)
+    xs = torch.arange(W, device=maps.device, dtype=torch.float64).repeat(H)
+    ys = torch.arange(H, device=maps.device, dtype=torch.float64).repeat_interleave(W)
+    return torch.stack([(w * xs).sum(1) / s, (w * ys).sum(1) / s], dim=1), h.argmax(dim=1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lib", default=os.path.join(ROOT, "2025_icra_multi_view_robot_pose_estimation_b200", "libmvgeo.so"))
+    ap.add_argument("--tag", default="r02")
+    ap.add_argument("--shapes", default="c2,native32,native16")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "decode_regimes.jsonl"))
+    ap.add_argument("--only", default="", help="dist:amp:beta — run a single cell (for ncu)")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--mode", type=int, default=1, help="1 global (default), 2 window, 0 none")
+    a = ap.parse_args()
+    lib = bind(a.lib)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    fout = open(a.out, "a")
+    only = a.only.split(":") if a.only else None
+    for name in a.shapes.split(","):
+        n_maps, H, W, dtype = SHAPES[name]
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        kp = torch.rand((n_maps, 2), generator=g, device=dev) * torch.tensor([W - 1.0, H - 1.0], device=dev)
+        blob = torch.empty((n_maps, H, W), dtype=dtype, device=dev)
+        assert lib.mvgeo_encode_gaussian(kp.data_ptr(), n_maps, H, W, 3.0, DT[dtype], blob.data_ptr(), st) == 0
+        maps = torch.empty_like(blob)
+        nbytes = maps.numel() * maps.element_size()
+        idx = torch.empty((n_maps,), dtype=torch.int32, device=dev)
+        peak, score = torch.empty((n_maps,), device=dev), torch.empty((n_maps,), device=dev)
+        kph, kps = torch.empty((n_maps, 2), device=dev), torch.empty((n_maps, 2), device=dev)
+        cells = [("blob", amp) for amp in AMPS] + [("uniform", 1.0)]
+        for dist, amp in cells:
+            if only and (dist != only[0] or float(only[1]) != amp):
+                continue
+            chunk = max(1, n_maps // 64)
+            for m0 in range(0, n_maps, chunk):  # no full-size fp32 temporary
+                sl = slice(m0, m0 + chunk)
+                if dist == "blob":
+                    noise = torch.randn(blob[sl].shape, generator=g, device=dev, dtype=torch.float32).mul_(0.01)
+                    maps[sl] = (blob[sl].float() * amp + noise).to(dtype)
+                else:
+                    maps[sl] = torch.rand(blob[sl].shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
+            for beta in BETAS:
+                if only and float(only[2]) != beta:
+                    continue
+
+                def run():
+                    rc = lib.mvgeo_decode(maps.data_ptr(), DT[dtype], n_maps, H, W, 1.0, 1.0, a.mode, beta, 3, 0, 1, 1, 0,
+                                          idx.data_ptr(), peak.data_ptr(), score.data_ptr(), kph.data_ptr(),
+                                          kps.data_ptr(), st)
+                    assert rc == 0, rc
+                for _ in range(3):
+                    run()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(a.iters):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); run(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                med = statistics.median(ts)
+                ns = min(n_maps, 96)
+                rs, ri = ref_soft(maps[:ns], beta)
+                err = (kps[:ns].double() - rs).abs().max().item() if a.mode == 1 else None
+                idx_ok = bool((idx[:ns].long() == ri).all()) if dist == "blob" else None  # ties make argmax of rand ambiguous in f64 only if equal
+                rec = {"lib": a.tag, "shape": name, "n_maps": n_maps, "H": H, "W": W, "dtype": str(dtype).split(".")[1],
+                       "dist": dist, "amp": amp, "beta": beta, "mode": a.mode, "us": med * 1e3,
+                       "gbs": nbytes / med / 1e6, "gbs_best": nbytes / min(ts) / 1e6, "soft_err_map_px": err,
+                       "idx_ok_sample": idx_ok}
+                print(json.dumps(rec), flush=True)
+                fout.write(json.dumps(rec) + "\n")
+                fout.flush()
+        del blob, maps
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,8 @@ struct BlockScratch {
   float val[kMaxWarps];
   int idx[kMaxWarps];
   float sum[3][kMaxWarps];
+  uint32_t key[kMaxWarps];
+  double dsum[3][kMaxWarps];
 };
 
 // Barrier over a group of NW warps. bar == 0 is __syncthreads() (the group must then be the whole
@@ -141,7 +143,9 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, BlockSc
 // (s, sx, sy) are the soft-arg-max sums RELATIVE TO THE HARD PEAK: sum w, sum w (x - px), sum w (y - py).
 __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map, float M, int best, float s,
                                               float sx, float sy, bool have_soft) {
-  const int64_t o = (map / p.k_inner) * p.out_stride + p.out_offset + (map % p.k_inner);
+  int64_t o = map;  // dense [n_maps] results: the common case, no 64-bit division
+  if (p.k_inner != 1 || p.out_stride != 1 || p.out_offset != 0)
+    o = (map / p.k_inner) * p.out_stride + p.out_offset + (map % p.k_inner);
   const int py = best / p.W, px = best - py * p.W;
   if (p.idx) p.idx[o] = best;
   if (p.peak) p.peak[o] = M;
@@ -157,8 +161,11 @@ __device__ __forceinline__ void write_outputs(const DecodeParams& p, int64_t map
       if (M != M) {
         qx = qy = __int_as_float(0x7fc00000);
       } else if (s > 0.f) {
-        qx = (float)(((double)px + (double)sx / (double)s) * p.scale_x);
-        qy = (float)(((double)py + (double)sy / (double)s) * p.scale_y);
+        // offset from the hard peak in float (relative error 6e-8 of an offset of a few pixels), position
+        // and scaling in double like the hard key-point
+        const float inv = 1.0f / s;
+        qx = (float)(((double)px + (double)(sx * inv)) * p.scale_x);
+        qy = (float)(((double)py + (double)(sy * inv)) * p.scale_y);
       }
     }
     p.kp_soft[2 * o] = qx;
@@ -191,22 +198,100 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // ----------------------------------------------------------------------------------------
 // A "slice" is the U chunks {(t*U + u)*NT + gt, u < U} that one consumer thread owns in tile t.
 
-// Online soft-arg-max state of one thread: sums of w = 2^(h*beta' + nb), nb = -(running max)*beta',
-// over the elements seen so far, with coordinates relative to the map centre (exact small floats).
-// Every sum is an f32x2 pair (even / odd element of each 2-element group) so that the streaming loop
-// runs on packed FFMA2 / FADD2: one issue slot per two elements; the halves are added in the epilogue.
+// Online soft-arg-max state of one thread: sums of w = 2^(h*beta' + nb), nb = -ref*beta', over the
+// elements of the current EPOCH, with coordinates relative to the map centre (exact small floats).
+// Every sum is an f32x2 pair (even / odd element of each 2-element group) so that the loop runs on
+// packed FFMA2 / FADD2: one issue slot per two elements.
+//
+// Epochs. The reference `ref` is NOT the running maximum (with a per-thread running maximum SOME lane
+// of a warp breaks its record in ~90% of the tiles and the whole warp pays a rescale: 15% of all issued
+// instructions). Floating point keeps its relative precision for weights far from 1, so an epoch lasts as
+// long as the slice maxima stay within kEpochWindow (log2 units) of ref. When a slice leaves the window
+// (the thread climbs the peak, or comes back down to the background after a climb) the epoch's sums are
+// folded, in DOUBLE, into the thread's per-map totals in shared memory and a new epoch starts at the new level.
+// This bounds the dynamic range inside the f32 accumulators: without it, once a thread has met the peak
+// every later background tile is rounded at the scale of the peak's first moment (lever arm to the map
+// centre: hundreds of pixels) — measured up to 3e-4 px when the background holds ~1e-3 of the weight.
+// Cost: nothing per element; the fold runs a handful of times per map in the threads that cross the peak.
+constexpr float kEpochWindow = 16.0f;
 struct SoftAcc {
-  float nb;      // -run_max * beta_log2e as rounded (the epilogue corrects with the SAME value)
-  f32x2 s, sx, sy;  // sum w, sum w (x0 - ox), sum w (y - oy), x0 = the chunk's first column
-  f32x2 sj;      // sum w i, i = index of the element's 2-element group inside its chunk
+  float nb;              // -ref * beta_log2e as rounded (the fold corrects with the SAME value)
+  float ref_hi, ref_lo;  // ref +- kEpochWindow / beta_log2e
+  f32x2 s, sx, sy;       // sum w, sum w (x0 - ox), sum w (y - oy), x0 = the chunk's first column
+  f32x2 sj;              // sum w i, i = index of the element's 2-element group inside its chunk
 };
+
+// Per-thread, per-map totals over the finished epochs: S, SX, SY relative to reference nb (32 bytes in
+// shared memory; touched only by the fold).
+struct SoftTotals {
+  double S, SX, SY;
+  float nb;  // +inf: empty
+};
+__device__ __forceinline__ void totals_store(uint32_t addr, const SoftTotals& t) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(t.S), "d"(t.SX) : "memory");
+  asm volatile("st.shared.f64 [%0+16], %1;" ::"r"(addr), "d"(t.SY) : "memory");
+  asm volatile("st.shared.f32 [%0+24], %1;" ::"r"(addr), "f"(t.nb) : "memory");
+}
+__device__ __forceinline__ SoftTotals totals_load(uint32_t addr) {
+  SoftTotals t;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(t.S), "=d"(t.SX) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(t.SY) : "r"(addr));
+  asm volatile("ld.shared.f32 %0, [%1+24];" : "=f"(t.nb) : "r"(addr));
+  return t;
+}
+// Fold the epoch held in `a` into the totals (common reference = the higher of the two, so the
+// scale factor is <= 1 and can only underflow to a truly negligible 0), and clear the epoch.
+__device__ __forceinline__ void epoch_fold(SoftAcc& a, uint32_t totals_addr) {
+  const float ts = sum2(a.s);
+  if (ts > 0.f) {  // an empty epoch (or one poisoned by +inf - +inf) adds nothing
+    float s_even, s_odd, h0, h1;
+    unpack2(a.s, s_even, s_odd);
+    const double S = (double)s_even + (double)s_odd;
+    unpack2(a.sx, h0, h1);
+    float j0, j1;
+    unpack2(a.sj, j0, j1);
+    // sum_j j*w_j over the chunks = 2 * sum_i i*(w_i.lo + w_i.hi) + sum_i w_i.hi
+    const double SX = ((double)h0 + (double)h1) + 2.0 * ((double)j0 + (double)j1) + (double)s_odd;
+    unpack2(a.sy, h0, h1);
+    const double SY = (double)h0 + (double)h1;
+    SoftTotals t = totals_load(totals_addr);
+    if (a.nb <= t.nb) {  // the epoch's reference is the higher one (nb = -ref*beta'): bring the totals to it
+      const double f = (double)ex2_approx(a.nb - t.nb);  // empty totals: nb = +inf -> f = 0
+      t.S = t.S * f + S;
+      t.SX = t.SX * f + SX;
+      t.SY = t.SY * f + SY;
+      t.nb = a.nb;
+    } else {
+      const double f = (double)ex2_approx(t.nb - a.nb);
+      t.S += S * f;
+      t.SX += SX * f;
+      t.SY += SY * f;
+    }
+    totals_store(totals_addr, t);
+  }
+  a.s = a.sx = a.sy = a.sj = 0ull;
+}
+
+// Order-preserving map float -> uint32 with NaN (any sign, any payload) on top, so that a warp-wide
+// maximum with torch's NaN-is-maximal rule is ONE redux.sync instruction.
+__device__ __forceinline__ uint32_t ord_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  if (v != v) return 0xffffffffu;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
 // G independent consumer groups per CTA (8/G warps each, own ring, own mbarriers, own named
 // barrier, own map sequence): small maps use G > 1 so that one group's latency-bound epilogue
 // overlaps the other groups' streaming. Producer warp 8+g (one elected lane) feeds group g.
 // Grid = one resident wave; group (blockIdx.x, g) walks maps blockIdx.x*G + g, +gridDim.x*G, ...
+#ifndef MVGEO_DEC_MINB
+#define MVGEO_DEC_MINB 2  // measured: 2 CTAs/SM without a register cap beat 3 CTAs/SM at 64 registers (spills)
+#endif
 template <int DT, int MODE, int U, int STAGES, int G>
-__global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_tma_kernel(const DecodeParams p) {
   using E = Elem<DT>;
   constexpr int PER = E::kPerChunk;
   constexpr int NW = kDecWarps / G;  // consumer warps per group
@@ -268,44 +353,52 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const 
   const int gt = tid - g * NT;  // thread index inside the group
   const int lw = gt >> 5;
   const int bar = 1 + g;
+  BlockScratch& scr = sc[g];
   const uint32_t my_s = ring_s + (uint32_t)gt * 16;  // this thread's first chunk of slot 0
+  // behind the rings: the raw chunks of every thread's best slice so far ([g][u][gt], 16 KB per CTA:
+  // the epilogue finds the first maximal element there, not in global memory), and every thread's
+  // tile-0 chunk positions ([g][2][gt] float4: computed once per CTA, the maps all have one shape)
+  const uint32_t cand_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + (uint32_t)(g * kTile + gt) * 16;
+  const uint32_t pos_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + (uint32_t)(g * 2 * NT + gt) * 16;
+  // ... and every thread's per-map soft-arg-max totals (32 bytes each)
+  const uint32_t tot_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 32 +
+                         (uint32_t)(g * NT + gt) * 32;
 
-  // Soft-arg-max geometry of this thread (the same for every map): position of chunk u of tile 0
-  // relative to the map centre, and the (row, column) advance from one tile to the next.
+  // Soft-arg-max geometry: coordinates are relative to the map centre; from one tile to the next a
+  // chunk advances by (step_y rows, step_x columns) with at most one row wrap.
   const float ox = 0.5f * (float)p.W, oy = 0.5f * (float)p.H, Wf = (float)p.W;
   const float x_hi = Wf - ox;  // first column value that belongs to the next row
-  float fx0[U], fy0[U];
-  float step_x = 0.f, step_y = 0.f;
-  if (MODE == MVGEO_SOFT_GLOBAL) {
+  const float step_y = (float)((kTile * PER) / p.W), step_x = (float)((kTile * PER) % p.W);
+  const f32x2 beta2 = pack2(p.beta_log2e, p.beta_log2e);
+  const float window = kEpochWindow / p.beta_log2e;
+  const float kNegInf = __int_as_float(0xff800000);
+
+  static_assert(U == 4, "positions are kept as two float4 per thread");
+  if (MODE == MVGEO_SOFT_GLOBAL) {  // position of chunk u of tile 0: private to the thread, no barrier needed
+    float px0[U], py0[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int e0 = (u * NT + gt) * PER;
       const int y0 = e0 / p.W;
-      fx0[u] = (float)(e0 - y0 * p.W) - ox;
-      fy0[u] = (float)y0 - oy;
+      px0[u] = (float)(e0 - y0 * p.W) - ox;
+      py0[u] = (float)y0 - oy;
     }
-    const int st = kTile * PER;
-    step_y = (float)(st / p.W);
-    step_x = (float)(st % p.W);
+    sts128(pos_s, make_uint4(__float_as_uint(px0[0]), __float_as_uint(px0[1]), __float_as_uint(px0[2]), __float_as_uint(px0[3])));
+    sts128(pos_s + NT * 16, make_uint4(__float_as_uint(py0[0]), __float_as_uint(py0[1]), __float_as_uint(py0[2]), __float_as_uint(py0[3])));
   }
-  const f32x2 beta2 = pack2(p.beta_log2e, p.beta_log2e);
 
   int s = 0;
   uint32_t ph = 0;
   for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
-    float run_max = __int_as_float(0xff800000);  // -inf
+    float run_max = kNegInf;
     int run_tile = gt < n ? 0 : -1;
-    uint4 run_v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) run_v[u] = E::neg_inf_chunk();  // an all -inf map resolves to index 0
-    SoftAcc a = {0.f, 0ull, 0ull, 0ull, 0ull};
+    SoftAcc a = {0.f, kNegInf, kNegInf, 0ull, 0ull, 0ull, 0ull};
+    if (MODE == MVGEO_SOFT_GLOBAL) totals_store(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
     float fx[U], fy[U];
     if (MODE == MVGEO_SOFT_GLOBAL) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        fx[u] = fx0[u];
-        fy[u] = fy0[u];
-      }
+      const uint4 qx = lds128(pos_s), qy = lds128(pos_s + NT * 16);
+      fx[0] = __uint_as_float(qx.x); fx[1] = __uint_as_float(qx.y); fx[2] = __uint_as_float(qx.z); fx[3] = __uint_as_float(qx.w);
+      fy[0] = __uint_as_float(qy.x); fy[1] = __uint_as_float(qy.y); fy[2] = __uint_as_float(qy.z); fy[3] = __uint_as_float(qy.w);
     }
 
     // One tile: wait for the slot, take the thread's slice into registers, arg-max bookkeeping,
@@ -325,7 +418,8 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const 
       // vertical (packed) maximum over the thread's slice, then ONE horizontal step and ONE
       // running-maximum update per tile. The slice maximum is canonicalised (+0.0f turns -0 into
       // +0) so that the update test is a bit comparison of max.NaN results: equal values, -0/+0
-      // and NaN/NaN all keep the FIRST slice.
+      // and NaN/NaN all keep the FIRST tile. Only the tile NUMBER is remembered (one predicated
+      // move); the epilogue re-reads the winning slice of the one thread that holds the maximum.
       uint32_t vm = E::vmax(v[0]);
 #pragma unroll
       for (int u = 1; u < U; ++u) vm = E::vmerge(vm, E::vmax(v[u]));
@@ -339,25 +433,24 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const 
         ph ^= 1;
       }
       const float nm = max_nan_f32(run_max, sm);
-      if (__float_as_uint(nm) != __float_as_uint(run_max)) {  // strictly better: remember the slice itself
+      if (__float_as_uint(nm) != __float_as_uint(run_max)) {  // strictly better: park the slice in shared memory
         run_tile = t;
 #pragma unroll
-        for (int u = 0; u < U; ++u) run_v[u] = v[u];
-        if (MODE == MVGEO_SOFT_GLOBAL) {
-          // new reference for the thread's weights: rescale what has been accumulated so far.
-          // (-inf or NaN maximum: reference 0; a NaN peak is reported as NaN whatever the sums hold)
-          const float nb2 = (nm > __int_as_float(0xff800000)) ? -nm * p.beta_log2e : 0.f;
-          const float r = run_max > __int_as_float(0xff800000) ? ex2_approx(nb2 - a.nb) : 0.f;
-          const f32x2 r2 = pack2(r, r);
-          a.s = mul2(a.s, r2);
-          a.sx = mul2(a.sx, r2);
-          a.sy = mul2(a.sy, r2);
-          a.sj = mul2(a.sj, r2);
-          a.nb = nb2;
-        }
+        for (int u = 0; u < U; ++u) sts128(cand_s + u * NT * 16, v[u]);
       }
       run_max = nm;
       if (MODE == MVGEO_SOFT_GLOBAL) {
+        // rare: the slice leaves the epoch's window (first finite slice, climbing the peak, coming back down)
+        // An epoch that began by CLIMBING (a genuine peak) ends when the slices come back down; an epoch
+        // that began at the first finite slice or by coming down has no lower bound: plain noise whose slice
+        // maxima wander by more than the window (uniform maps at large beta) would otherwise fold in most tiles.
+        if (sm > a.ref_hi || (sm < a.ref_lo && sm > kNegInf)) {
+          const bool climbed = sm > a.ref_hi && a.ref_hi > kNegInf;
+          epoch_fold(a, tot_s);
+          a.nb = -sm * p.beta_log2e;
+          a.ref_hi = sm + window;
+          a.ref_lo = climbed ? sm - window : kNegInf;
+        }
         const f32x2 nb2 = pack2(a.nb, a.nb);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -395,46 +488,87 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G) decode_tma_kernel(const 
     if (n_full < n_tiles) tile_body(std::false_type{}, n_full);
 
     // ------------------------------ per-map epilogue (consumers of this group only) ------------
-    // first maximal element inside the winning slice, straight from the registers that kept it
-    // (no global re-read on the latency-critical path). Descending loops: the lowest index sticks.
-    float my_val = run_max;
+    // 1. the maximum: one redux.sync per warp on order-preserving keys, then NW values through smem
+    const uint32_t wk = __reduce_max_sync(0xffffffffu, ord_key(run_max));
+    if (lane == 0) scr.key[lw] = wk;
+    group_sync<NW>(bar);
+    uint32_t mk = scr.key[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) mk = max(mk, scr.key[w]);
+    const float M = ord_val(mk);
+    // 2. the first maximal element: only threads that hold the maximum look at their winning slice
+    //    (parked in shared memory by the streaming loop), lowest index wins
     int my_idx = 0x7fffffff;
-    if (run_tile >= 0) {
-      const bool isn = (run_max != run_max);
+    const bool isn = (M != M);
+    // (an all -inf map parked nothing: every element is maximal and index 0 wins, see below)
+    if (run_tile >= 0 && M != kNegInf && (isn ? (run_max != run_max) : (__float_as_uint(run_max) == __float_as_uint(M)))) {
 #pragma unroll
-      for (int u = U - 1; u >= 0; --u) {
+      for (int u = U - 1; u >= 0; --u) {  // descending: the lowest index sticks
         const int c = (run_tile * U + u) * NT + gt;
+        if (c < n) {
+          const uint4 ch = lds128(cand_s + u * NT * 16);
 #pragma unroll
-        for (int j = PER - 1; j >= 0; --j) {
-          const float e = E::get(run_v[u], j);
-          const bool hit = (c < n) && (isn ? (e != e) : (e == run_max));
-          if (hit) my_idx = c * PER + j;
+          for (int j = PER - 1; j >= 0; --j) {
+            const float e = E::get(ch, j);
+            if (isn ? (e != e) : (e == M)) my_idx = c * PER + j;
+          }
         }
       }
     }
-    block_argmax<NW>(my_val, my_idx, sc[g], bar, lw);
-    const float M = my_val;
-    const int best = my_idx;
-    const int py = best / p.W, px = best - py * p.W;
-
+    const int wi = __reduce_min_sync(0xffffffffu, my_idx);
+    if (lane == 0) scr.idx[lw] = wi;
+    // 3. soft-arg-max sums, rescaled from the thread's reference to the true maximum. The moments are
+    //    still relative to the map centre (the peak position is not reduced yet) and the thread that holds
+    //    the peak carries a lever arm of hundreds of pixels that cancels in the end: the per-map
+    //    reduction runs in double (a few instructions per thread and MAP, nothing per element).
     float ss = 0.f, sx = 0.f, sy = 0.f;
     if (MODE == MVGEO_SOFT_GLOBAL) {
-      const float ts = sum2(a.s);
-      if (ts > 0.f) {
-        // 2^((m_t - M) beta') formed with the thread's own rounded reference, so the rounding of nb
-        // cancels exactly; then shift the first moments from the map centre to the hard peak.
-        const float r = ex2_approx(fmaf(-M, p.beta_log2e, -a.nb));
-        ss = ts * r;
-        float s_even, s_odd;
-        unpack2(a.s, s_even, s_odd);
-        sx = fmaf(ox - (float)px, ss, (sum2(a.sx) + fmaf(2.0f, sum2(a.sj), s_odd)) * r);
-        sy = fmaf(oy - (float)py, ss, sum2(a.sy) * r);
+      double ds = 0.0, dx = 0.0, dy = 0.0;
+      epoch_fold(a, tot_s);  // the last epoch
+      const SoftTotals t = totals_load(tot_s);
+      if (t.S > 0.0) {
+        // 2^((ref - M) beta') formed with the rounded nb the weights were formed with: its rounding cancels
+        const double r = (double)ex2_approx(fmaf(-M, p.beta_log2e, -t.nb));
+        ds = t.S * r;
+        dx = t.SX * r;
+        dy = t.SY * r;
       }
-    } else if (MODE == MVGEO_SOFT_WINDOW) {
-      window_accumulate<DT, NT>(p, map_ptr(p, map), M, px, py, gt, ss, sx, sy);
+      ds = warp_sum_f64(ds);
+      dx = warp_sum_f64(dx);
+      dy = warp_sum_f64(dy);
+      if (lane == 0) {
+        scr.dsum[0][lw] = ds;
+        scr.dsum[1][lw] = dx;
+        scr.dsum[2][lw] = dy;
+      }
     }
-    if (MODE != MVGEO_SOFT_NONE) block_sum3<NW>(ss, sx, sy, sc[g], bar, lw);
+    group_sync<NW>(bar);
+    int best = scr.idx[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) best = min(best, scr.idx[w]);
+    if (best == 0x7fffffff) best = 0;  // all -inf map: nothing was ever parked; every element is maximal, the first wins
+    const int py = best / p.W, px = best - py * p.W;
+    if (MODE == MVGEO_SOFT_WINDOW) {
+      window_accumulate<DT, NT>(p, map_ptr(p, map), M, px, py, gt, ss, sx, sy);
+      block_sum3<NW>(ss, sx, sy, scr, bar, lw);
+    } else if (MODE == MVGEO_SOFT_GLOBAL) {
+      if (gt == 0) {
+        double ds = 0.0, dx = 0.0, dy = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {  // fixed order: deterministic
+          ds += scr.dsum[0][w];
+          dx += scr.dsum[1][w];
+          dy += scr.dsum[2][w];
+        }
+        // shift the first moments from the map centre to the hard peak, then leave double
+        ss = (float)ds;
+        sx = (float)(dx + (double)(ox - (float)px) * ds);
+        sy = (float)(dy + (double)(oy - (float)py) * ds);
+      }
+    }
     if (gt == 0) write_outputs(p, map, M, best, ss, sx, sy, MODE != MVGEO_SOFT_NONE);
+    // scr.key is rewritten only after the next map's streaming loop; scr.idx / scr.sum only after
+    // the next map's first barrier: no trailing barrier needed.
   }
 }
 
@@ -486,35 +620,43 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 
 // Streaming-kernel configuration: tile = 256*kTmaU chunks over the CTA's groups, kTmaStages-deep ring.
 #ifndef MVGEO_TMA_U
-#define MVGEO_TMA_U 2
+#define MVGEO_TMA_U 4
 #endif
 #ifndef MVGEO_TMA_STAGES
 #define MVGEO_TMA_STAGES 4
 #endif
+#ifndef MVGEO_G4_MAX
+#define MVGEO_G4_MAX (112 * 1024)
+#endif
+#ifndef MVGEO_G2_MAX
+#define MVGEO_G2_MAX (160 * 1024)
+#endif
 constexpr int kTmaU = MVGEO_TMA_U;
 constexpr int kTmaStages = MVGEO_TMA_STAGES;
-constexpr size_t kRingBytes = (size_t)kTmaStages * kTmaU * kDecThreads * 16;  // 32 KB: under the 48 KB default limit
-static_assert(kRingBytes <= 48 * 1024, "the ring must fit the default dynamic shared-memory limit (no function attribute)");
+// per CTA: the rings, one tile of parked candidate slices, two float4 of chunk positions and the 32-byte
+// soft-arg-max totals per thread
+constexpr size_t kRingBytes = (size_t)(kTmaStages + 1) * kTmaU * kDecThreads * 16 + (size_t)kDecThreads * 64;
 constexpr int kMaxDevices = 64;
 
 template <int DT, int MODE, int G>
 static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
   auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G>;
   // Resident-wave size per (instantiation, device): a pure function of its key, cached because the
-  // occupancy query costs microseconds on a latency-bound call. No function attribute is ever set
-  // (the ring fits the default limit), so concurrent callers cannot disturb one another; a racing
-  // thread recomputes and stores the same value.
+  // occupancy query costs microseconds on a latency-bound call. The dynamic shared-memory opt-in is
+  // set to the SAME constant by every caller (the ring never changes size), so concurrent callers
+  // cannot disturb one another; a racing thread recomputes and stores the same value.
   static std::atomic<int> cache[kMaxDevices];
   int dev = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
-  int resident_ctas = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  int resident_ctas = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load(std::memory_order_acquire) : 0;
   if (resident_ctas == 0) {
+    MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingBytes));
     int sms = 0, per_sm = 0;
     MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, kRingBytes));
     if (per_sm < 1) return MVGEO_EUNSUPPORTED;
     resident_ctas = sms * per_sm;
-    if (dev >= 0 && dev < kMaxDevices) cache[dev].store(resident_ctas, std::memory_order_relaxed);
+    if (dev >= 0 && dev < kMaxDevices) cache[dev].store(resident_ctas, std::memory_order_release);
   }
   const int64_t wanted = (p.n_maps + G - 1) / G;
   const unsigned grid = (unsigned)(wanted < resident_ctas ? wanted : resident_ctas);
@@ -596,7 +738,7 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.chunks_per_map = vec ? (int)(p.map_bytes / 16) : 0;
   // small maps -> several consumer groups per CTA, one map stream each (epilogues overlap):
   // 4 up to 112 KB (native 128x128 fp32, C1), 2 up to 160 KB (C2 / C3), measured; larger: one group.
-  const int groups = p.map_bytes <= 112 * 1024 ? 4 : (p.map_bytes <= 160 * 1024 ? 2 : 1);
+  const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
     case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, groups, st);

@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(kPnpThreads)
   int n = 0;
   for (int k = 0; k < K; ++k) {
     const float wt = wp ? wp[k] : 1.0f;
-    if ((wt >= min_weight) && isfinite(kpp[2 * k]) && isfinite(kpp[2 * k + 1])) {
+    // a point takes part only if its weight passes, and BOTH its image and object coordinates are finite
+    // (X_tri is NaN for under-observed key-points: one NaN would turn every cost comparison false)
+    if ((wt >= min_weight) && isfinite(kpp[2 * k]) && isfinite(kpp[2 * k + 1]) && isfinite(Xp[3 * k]) &&
+        isfinite(Xp[3 * k + 1]) && isfinite(Xp[3 * k + 2])) {
       valid |= 1u << k;
       ++n;
     }
@@ -273,9 +276,16 @@ __global__ void __launch_bounds__(kPnpThreads)
         lambda *= 10.0;
       }
       if (!accepted) {  // no downhill step at any damping: at a minimum to working precision
-        st |= 2;
+        if (isfinite(cost)) st |= 2;  // a non-finite cost (prior puts a point on the camera plane) is not convergence
         break;
       }
+    }
+    if (!isfinite(cost)) {  // failed solve: hand back the prior, as the header promises
+      st &= ~2;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) R[j] = (double)cam.R[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t[j] = (double)cam.t[j];
     }
     const double tn2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
     if (tn2 > 0.25 && tn2 < 25.0) st |= 4;  // 0.5 m < |t| < 5 m (Franka_research3_model_train.ipynb:3696-3701)

@@ -8,7 +8,8 @@ CPU tests), < 1 KB per frame.
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -22,6 +23,42 @@ def frame_range(n_frames: int, rank: int, world_size: int) -> Tuple[int, int]:
     first_big = world_size - rem  # ranks >= first_big get base + 1 frames
     begin = rank * base + max(0, rank - first_big)
     return begin, begin + base + (1 if rank >= first_big else 0)
+
+
+def gpu_local_cpus(device_index: int) -> List[int]:
+    """CPUs on the NUMA node / socket the GPU hangs off (NVML's ideal CPU affinity); [] if unknown."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        return [c for c in cpus if c < n_cpu]
+    except Exception:
+        return []
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin the calling thread (and the threads it creates afterwards) to the CPUs next to GPU
+    `device_index`, so that pinned host buffers allocated from now on are first-touched on that
+    socket and H2D copies do not cross the inter-socket link. One process per GPU (torchrun does not
+    bind ranks): call it right after torch.cuda.set_device, BEFORE allocating pinned memory.
+    Returns the CPU list it bound to, or None when the topology is unknown or the binding is refused
+    (cgroup cpusets)."""
+    cpus = gpu_local_cpus(device_index)
+    if not cpus:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0)
+        target = sorted(set(cpus) & set(allowed))
+        if not target:
+            return None
+        os.sched_setaffinity(0, target)
+        return target
+    except Exception:
+        return None
 
 
 def gather_frames(local: Dict[str, torch.Tensor], n_frames: int, group=None) -> Dict[str, torch.Tensor]:

@@ -10,7 +10,7 @@ from .robots import Chain, view_rotation, VIEW_EULER_ZYX_DEG
 from .rig import CameraRig, ZEDX_FHD1200, load_conf_calibration, rodrigues
 from . import ops, compat, sharding
 from .graphed import GraphedPipeline
-from .ops import (decode_heatmaps, triangulate, pnp_refine, quat_mean, forward_kinematics, project_points, undistort_points, fk_reproj_loss,
-                  encode_gaussian, heatmap_mse_loss, pipeline, HostPipeline, alloc_outputs, DecodeResult)
+from .ops import (decode_heatmaps, triangulate, pnp_refine, pnp_solve, quat_mean, forward_kinematics, project_points, undistort_points, fk_reproj_loss,
+                  encode_gaussian, heatmap_mse_loss, decode_and_mse, pipeline, HostPipeline, alloc_outputs, DecodeResult)
 
 __version__ = "0.1.0"

@@ -71,8 +71,10 @@ _SIGNATURES = {
     "mvgeo_geometry": ([_vp, _vp, _vp, C.POINTER(ChainStruct), _vp, _i64, _vp, _vp, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp,
                         _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_pnp_refine": ([_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "mvgeo_pnp_solve": ([_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_encode_gaussian": ([_vp, _i64, _i, _i, _f, _i, _vp, _vp], _i),
     "mvgeo_heatmap_mse": ([_vp, _i, _vp, _i64, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp], _i),
+    "mvgeo_decode_mse": ([_vp, _i, _i64, _i, _i, _d, _d, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "mvgeo_pipeline": ([C.POINTER(PipelineCfg), _vp, _i64, _vp, C.POINTER(ChainStruct), _vp, _vp, _vp,
                         C.POINTER(PipelineOut), _vp], _i),
     "mvgeo_pipeline_views": ([C.POINTER(PipelineCfg), C.POINTER(_vp), _i64, _vp, C.POINTER(ChainStruct), _vp, _vp, _vp,

@@ -70,6 +70,38 @@ def _project_single(coords_3d, rvec, tvec, camera_matrix, dist_coeffs):
     return ops.project_points(X, rig)[0, 0].cpu().numpy()
 
 
+def _estimate_camera_pose(robot, gate, predicted_angles, predicted_heatmaps, camera_matrix, dist_coeffs, selected_view,
+                          original_image_size, confidence_threshold):
+    """estimate_camera_pose (model/Fr5_model_train.ipynb:4707-4753; FR3 variant with the 0.5-5 m plausibility gate,
+    model/Franka_research3_model_train.ipynb:3667-3708): FK of the predicted angles -> 3-D object points; decode the
+    predicted heat-maps -> 2-D key-points + sigmoid scores; keep score >= threshold (refuse below 4 points, :4728);
+    pose by consensus PnP (mvgeo_pnp_solve in place of cv2.solvePnPRansac(..., SOLVEPNP_EPNP), :4735-4741).
+    Returns (rvec (3,1) float64, tvec (3,1) float64, object_points_3d np.float32[K,3], image_points_2d np.float32[K,2]);
+    rvec = tvec = None when the reference would return None. One device round trip."""
+    dev = _device()
+    chain = Chain.builtin(robot)
+    ang = predicted_angles.detach().cpu().numpy() if isinstance(predicted_angles, torch.Tensor) else np.asarray(predicted_angles)
+    q = torch.as_tensor(np.asarray(ang, dtype=np.float32).reshape(-1)[: chain.n_joints].reshape(1, -1)).to(dev)
+    Rv = np.asarray(view_rotation(robot, selected_view), dtype=np.float32)[None]
+    X = ops.forward_kinematics(chain, q, Rv)[:, 0]                                   # (1,K,3)
+    hm = predicted_heatmaps if isinstance(predicted_heatmaps, torch.Tensor) else torch.as_tensor(np.asarray(predicted_heatmaps))
+    r = ops.decode_heatmaps(hm.detach().to(dev), original_image_size, soft=None, apply_sigmoid=True)
+    Kc = np.asarray(camera_matrix, dtype=np.float64).reshape(1, 3, 3)
+    d = np.zeros((1, 5)) if dist_coeffs is None else np.asarray(dist_coeffs, dtype=np.float64).reshape(-1)[:5][None]
+    rig = CameraRig(Kc, d, np.eye(3)[None], np.zeros((1, 3)))
+    rvec, tvec, rms, status, inl = ops.pnp_solve(X, r.kp_hard[None, None], rig, r.score[None, None],
+                                                 min_weight=float(confidence_threshold))
+    packed = torch.cat([X.reshape(-1), r.kp_hard.reshape(-1), rvec.reshape(-1), tvec.reshape(-1),
+                        status.reshape(-1).float()]).cpu().numpy()                  # ONE device-to-host copy
+    K = chain.n_points
+    obj = packed[: 3 * K].reshape(K, 3).astype(np.float32)
+    img = packed[3 * K: 5 * K].reshape(K, 2).astype(np.float32)
+    rv, tv, st = packed[5 * K: 5 * K + 3], packed[5 * K + 3: 5 * K + 6], int(packed[5 * K + 6])
+    if not (st & 1) or (gate and not (st & 4)):
+        return None, None, obj, img
+    return rv.astype(np.float64).reshape(3, 1), tv.astype(np.float64).reshape(3, 1), obj, img
+
+
 def _make_fr3():
     chain = None
 
@@ -85,8 +117,15 @@ def _make_fr3():
         t = [aruco_result["tvec_x"], aruco_result["tvec_y"], aruco_result["tvec_z"]]
         return _project_single(coords_3d, r, t, camera_matrix, dist_coeffs)
 
+    def estimate_camera_pose(predicted_angles, predicted_heatmaps, camera_matrix, dist_coeffs, selected_view,
+                             original_image_size, confidence_threshold=0.1):
+        """model/Franka_research3_model_train.ipynb:3667-3708 (with the 0.5 m < |t| < 5 m gate, :3696-3701)."""
+        return _estimate_camera_pose("fr3", True, predicted_angles, predicted_heatmaps, camera_matrix, dist_coeffs,
+                                     selected_view, original_image_size, confidence_threshold)
+
     return SimpleNamespace(angle_to_joint_coordinate=angle_to_joint_coordinate,
-                           joint_coordinate_to_pixel_plane=joint_coordinate_to_pixel_plane)
+                           joint_coordinate_to_pixel_plane=joint_coordinate_to_pixel_plane,
+                           estimate_camera_pose=estimate_camera_pose)
 
 
 def _make_fr5():
@@ -104,8 +143,15 @@ def _make_fr5():
         t = np.array([aruco_result[k] for k in ("tvec_x", "tvec_y", "tvec_z")], dtype=np.float32)
         return _project_single(joint_coords, r, t, camera_matrix, dist_coeffs)
 
+    def estimate_camera_pose(predicted_angles, predicted_heatmaps, camera_matrix, dist_coeffs, selected_view,
+                             original_image_size, confidence_threshold=0.1):
+        """model/Fr5_model_train.ipynb:4707-4753 (no distance gate in this variant)."""
+        return _estimate_camera_pose("fr5", False, predicted_angles, predicted_heatmaps, camera_matrix, dist_coeffs,
+                                     selected_view, original_image_size, confidence_threshold)
+
     return SimpleNamespace(angle_to_joint_coordinate=angle_to_joint_coordinate,
-                           joint_coordinate_to_pixel_plane=joint_coordinate_to_pixel_plane)
+                           joint_coordinate_to_pixel_plane=joint_coordinate_to_pixel_plane,
+                           estimate_camera_pose=estimate_camera_pose)
 
 
 def _make_meca500():
@@ -147,20 +193,34 @@ class ForwardKinematics:
 
 def project_3d_to_2d(joint_3d, camera_matrix, dist_coeffs=None, rvec=None, tvec=None):
     """model/MV-model.ipynb:879-899: (B,J,3) -> torch.float32 (B,J,2); rvec / tvec are per-batch
-    lists (None = zero rotation / translation)."""
+    lists (None = zero rotation / translation). The per-item poses become the "views" of one rig, so the whole
+    batch is ONE launch (chunks of 16 items: MVGEO_MAX_VIEWS) instead of one launch + sync per item."""
     X = torch.as_tensor(np.asarray(joint_3d), dtype=torch.float32)
-    out = []
-    for b in range(X.shape[0]):
-        r = np.zeros(3) if rvec is None else np.asarray(rvec[b], dtype=np.float64).reshape(3)
-        t = np.zeros(3) if tvec is None else np.asarray(tvec[b], dtype=np.float64).reshape(3)
-        out.append(_project_single(X[b].numpy(), r, t, camera_matrix, dist_coeffs))
-    return torch.tensor(np.stack(out), dtype=torch.float32)
+    Bn = int(X.shape[0])
+    K = np.asarray(camera_matrix, dtype=np.float64).reshape(3, 3)
+    d = np.zeros(5) if dist_coeffs is None else np.asarray(dist_coeffs, dtype=np.float64).reshape(-1)[:5]
+    dev = _device()
+    Xd = X.to(dev)
+    out = torch.empty((Bn, X.shape[1], 2), dtype=torch.float32, device=dev)
+    for b0 in range(0, Bn, 16):
+        n = min(16, Bn - b0)
+        recs = []
+        for b in range(b0, b0 + n):
+            r = np.zeros(3) if rvec is None else np.asarray(rvec[b], dtype=np.float64).reshape(3)
+            t = np.zeros(3) if tvec is None else np.asarray(tvec[b], dtype=np.float64).reshape(3)
+            recs.append(dict(rvec_x=r[0], rvec_y=r[1], rvec_z=r[2], tvec_x=t[0], tvec_y=t[1], tvec_z=t[2]))
+        rig = CameraRig.from_aruco(recs, np.broadcast_to(K, (n, 3, 3)), np.broadcast_to(d, (n, 5)))
+        out[b0:b0 + n] = ops.project_points(Xd[b0:b0 + n].unsqueeze(0).contiguous(), rig)[0]   # X per "view"
+    return out.cpu()
 
 
-def robot_pose_loss(pred, gt_keypoints=None, gt_angles=None, lambda_kp=1.0, lambda_angle=1.0, lambda_fk=1.0):
-    """model/MV-model.ipynb:942-950, unchanged in form; the three terms are plain MSEs on
-    tensors the caller already holds. For a FK term that is DIFFERENTIABLE in the angles use
-    ops.fk_reproj_loss (the reference's proj_2d is detached, MV-model.ipynb:874,899)."""
+def robot_pose_loss(pred, gt_keypoints=None, gt_angles=None, lambda_kp=1.0, lambda_angle=1.0, lambda_fk=1.0, *,
+                    chain=None, cams=None, R_view=None):
+    """model/MV-model.ipynb:942-950, unchanged in form: key-point MSE + angle MSE + FK-consistency MSE on
+    pred['proj_2d'] (which the reference computes detached, MV-model.ipynb:874,899).
+    Extension (keyword-only, absent in the reference): when pred has no 'proj_2d' and a `chain` plus one camera
+    (`cams`: CameraRig with a single view) are given, the FK term is computed from pred['angles'] by
+    mvgeo_fk_reproj_fwd/bwd — same value, but DIFFERENTIABLE in the angles."""
     import torch.nn.functional as F
 
     loss = 0.0
@@ -170,6 +230,12 @@ def robot_pose_loss(pred, gt_keypoints=None, gt_angles=None, lambda_kp=1.0, lamb
         loss = loss + lambda_angle * F.mse_loss(pred["angles"], gt_angles)
     if gt_keypoints is not None and pred.get("proj_2d") is not None:
         loss = loss + lambda_fk * F.mse_loss(pred["proj_2d"], gt_keypoints)
+    elif gt_keypoints is not None and chain is not None and cams is not None:
+        dev = _device()
+        q = pred["angles"].to(dev, dtype=torch.float32)
+        gt = gt_keypoints.to(dev, dtype=torch.float32).unsqueeze(1)                   # (B,1,J,2)
+        fk, _, _, _ = ops.fk_reproj_loss(chain, q, cams, gt.contiguous(), R_view, lam=float(lambda_fk))
+        loss = loss + fk.to(pred["angles"].device)
     return loss
 
 

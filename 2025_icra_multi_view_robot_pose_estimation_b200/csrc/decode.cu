@@ -59,6 +59,10 @@ struct DecodeParams {
   float* score;
   float* kp_hard;
   float* kp_soft;
+  // fused heat-map MSE against on-the-fly Gaussian targets (decode_tma_kernel<..., MSE = true>)
+  const float* mse_kp;   // [n_maps, 2] target centres in map pixels (non-finite: all-zero target)
+  float mse_k;           // log2(e) / (2 sigma^2)
+  float* mse_partial;    // [n_maps] sum over the map of (pred - target)^2
 };
 
 // Map m in result order [B, V, K] -> its first byte. With one base pointer the maps are dense.
@@ -290,8 +294,13 @@ __device__ __forceinline__ float ord_val(uint32_t k) {
 #ifndef MVGEO_DEC_MINB
 #define MVGEO_DEC_MINB 2  // measured: 2 CTAs/SM without a register cap beat 3 CTAs/SM at 64 registers (spills)
 #endif
-template <int DT, int MODE, int U, int STAGES, int G>
+// MSE: the same pass also accumulates sum (pred - g)^2 per map against the separable Gaussian target
+// g(x, y) = ex[x] * ey[y] built in shared memory per map (W + H exponentials, as csrc/encode.cu does) — the
+// training step's heat-map loss (nn.MSELoss, model/MvRoPose_FR3.py:846-847) and the decode of the same
+// prediction read the maps ONCE.
+template <int DT, int MODE, int U, int STAGES, int G, bool MSE = false>
 __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_tma_kernel(const DecodeParams p) {
+  static_assert(!MSE || MODE == MVGEO_SOFT_NONE, "the fused loss pass decodes the hard peak only");
   using E = Elem<DT>;
   constexpr int PER = E::kPerChunk;
   constexpr int NW = kDecWarps / G;  // consumer warps per group
@@ -373,6 +382,11 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
   const float window = kEpochWindow / p.beta_log2e;
   const float kNegInf = __int_as_float(0xff800000);
 
+  // MSE: behind the totals, one table of ex[0..Wp) and ey[0..H) per consumer group
+  const int Wp = (p.W + 3) & ~3;
+  const uint32_t tab_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 64 +
+                         (uint32_t)g * (uint32_t)(Wp + ((p.H + 3) & ~3)) * 4;
+  const int mse_step_y = (kTile * PER) / p.W, mse_step_x = (kTile * PER) % p.W;
   static_assert(U == 4, "positions are kept as two float4 per thread");
   if (MODE == MVGEO_SOFT_GLOBAL) {  // position of chunk u of tile 0: private to the thread, no barrier needed
     float px0[U], py0[U];
@@ -394,6 +408,25 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
     int run_tile = gt < n ? 0 : -1;
     SoftAcc a = {0.f, kNegInf, kNegInf, 0ull, 0ull, 0ull, 0ull};
     if (MODE == MVGEO_SOFT_GLOBAL) totals_store(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
+    int ix[U], iy[U];
+    f32x2 mse_acc = 0ull;
+    if (MSE) {
+      // the map's separable Gaussian tables (consumers of this group only; the previous map's last table
+      // reads are behind its epilogue barriers)
+      const float cx = p.mse_kp[2 * map], cy = p.mse_kp[2 * map + 1];
+      const bool okc = isfinite(cx) && isfinite(cy);
+      for (int i = gt; i < p.W + p.H; i += NT) {
+        const float d = i < p.W ? (float)i - cx : (float)(i - p.W) - cy;
+        sts32f(tab_s + (uint32_t)(i < p.W ? i : Wp + i - p.W) * 4, okc ? ex2_approx(-d * d * p.mse_k) : 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e0 = (u * NT + gt) * PER;
+        iy[u] = e0 / p.W;
+        ix[u] = e0 - iy[u] * p.W;
+      }
+      group_sync<NW>(bar);
+    }
     float fx[U], fy[U];
     if (MODE == MVGEO_SOFT_GLOBAL) {
       const uint4 qx = lds128(pos_s), qy = lds128(pos_s + NT * 16);
@@ -439,6 +472,32 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
         for (int u = 0; u < U; ++u) sts128(cand_s + u * NT * 16, v[u]);
       }
       run_max = nm;
+      if (MSE) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (FULL || t * kTile + u * NT + gt < n) {  // padding must not reach the loss
+            const float gy = -lds32f(tab_s + (uint32_t)(Wp + iy[u]) * 4);
+            const f32x2 ngy = pack2(gy, gy);
+#pragma unroll
+            for (int h = 0; h < PER / 4; ++h) {
+              const uint4 gx = lds128(tab_s + (uint32_t)(ix[u] + 4 * h) * 4);
+              float lo, hi;
+              E::pair(v[u], 2 * h, lo, hi);
+              f32x2 d = fma2(pack2(__uint_as_float(gx.x), __uint_as_float(gx.y)), ngy, pack2(lo, hi));
+              mse_acc = fma2(d, d, mse_acc);
+              E::pair(v[u], 2 * h + 1, lo, hi);
+              d = fma2(pack2(__uint_as_float(gx.z), __uint_as_float(gx.w)), ngy, pack2(lo, hi));
+              mse_acc = fma2(d, d, mse_acc);
+            }
+          }
+          ix[u] += mse_step_x;
+          iy[u] += mse_step_y;
+          if (ix[u] >= p.W) {
+            ix[u] -= p.W;
+            ++iy[u];
+          }
+        }
+      }
       if (MODE == MVGEO_SOFT_GLOBAL) {
         // rare: the slice leaves the epoch's window (first finite slice, climbing the peak, coming back down)
         // An epoch that began by CLIMBING (a genuine peak) ends when the slices come back down; an epoch
@@ -517,6 +576,10 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
     }
     const int wi = __reduce_min_sync(0xffffffffu, my_idx);
     if (lane == 0) scr.idx[lw] = wi;
+    if (MSE) {
+      const float m = warp_sum(sum2(mse_acc));
+      if (lane == 0) scr.sum[0][lw] = m;
+    }
     // 3. soft-arg-max sums, rescaled from the thread's reference to the true maximum. The moments are
     //    still relative to the map centre (the peak position is not reduced yet) and the thread that holds
     //    the peak carries a lever arm of hundreds of pixels that cancels in the end: the per-map
@@ -565,6 +628,12 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
         sx = (float)(dx + (double)(ox - (float)px) * ds);
         sy = (float)(dy + (double)(oy - (float)py) * ds);
       }
+    }
+    if (MSE && gt == 0) {
+      float m = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) m += scr.sum[0][w];  // fixed order: deterministic
+      p.mse_partial[map] = m;
     }
     if (gt == 0) write_outputs(p, map, M, best, ss, sx, sy, MODE != MVGEO_SOFT_NONE);
     // scr.key is rewritten only after the next map's streaming loop; scr.idx / scr.sum only after
@@ -638,29 +707,35 @@ constexpr int kTmaStages = MVGEO_TMA_STAGES;
 constexpr size_t kRingBytes = (size_t)(kTmaStages + 1) * kTmaU * kDecThreads * 16 + (size_t)kDecThreads * 64;
 constexpr int kMaxDevices = 64;
 
-template <int DT, int MODE, int G>
+constexpr size_t kMseTableMax = 16 * 1024;  // shared memory of the fused loss pass's Gaussian tables (2 CTAs/SM still fit)
+
+template <int DT, int MODE, int G, bool MSE = false>
 static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
-  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G>;
+  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G, MSE>;
   // Resident-wave size per (instantiation, device): a pure function of its key, cached because the
   // occupancy query costs microseconds on a latency-bound call. The dynamic shared-memory opt-in is
   // set to the SAME constant by every caller (the ring never changes size), so concurrent callers
   // cannot disturb one another; a racing thread recomputes and stores the same value.
+  constexpr size_t kSmemMax = kRingBytes + (MSE ? kMseTableMax : 0);
+  const size_t smem = kSmemMax;  // constant per instantiation: the cached occupancy is exact
+  if (MSE && (size_t)G * (((p.W + 3) & ~3) + ((p.H + 3) & ~3)) * 4 > kMseTableMax)
+    return MVGEO_EUNSUPPORTED;  // very wide / tall maps: use the two separate passes
   static std::atomic<int> cache[kMaxDevices];
   int dev = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
   int resident_ctas = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load(std::memory_order_acquire) : 0;
   if (resident_ctas == 0) {
-    MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingBytes));
+    MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     int sms = 0, per_sm = 0;
     MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, kRingBytes));
+    MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, kSmemMax));
     if (per_sm < 1) return MVGEO_EUNSUPPORTED;
     resident_ctas = sms * per_sm;
     if (dev >= 0 && dev < kMaxDevices) cache[dev].store(resident_ctas, std::memory_order_release);
   }
   const int64_t wanted = (p.n_maps + G - 1) / G;
   const unsigned grid = (unsigned)(wanted < resident_ctas ? wanted : resident_ctas);
-  kern<<<grid, kDecThreads + 32 * G, kRingBytes, st>>>(p);
+  kern<<<grid, kDecThreads + 32 * G, smem, st>>>(p);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }
@@ -759,6 +834,63 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
   const void* one[1] = {maps};  // NULL is reported by decode_impl after the size / enum checks
   return decode_impl(one, 1, 1, dtype, n_maps, H, W, scale_x, scale_y, soft_mode, beta, window_radius, apply_sigmoid,
                      k_inner, out_stride, out_offset, idx, peak, score, kp_hard, kp_soft, stream);
+}
+
+namespace mvgeo {
+int finish_mse(const float* partial, int64_t n_maps, double N, float weight, float* loss, cudaStream_t st);  // encode.cu
+
+template <int DT>
+static int launch_decode_mse(const DecodeParams& p, int groups, cudaStream_t st) {
+  switch (groups) {
+    case 4: return launch_persistent<DT, MVGEO_SOFT_NONE, 4, true>(p, st);
+    case 2: return launch_persistent<DT, MVGEO_SOFT_NONE, 2, true>(p, st);
+    default: return launch_persistent<DT, MVGEO_SOFT_NONE, 1, true>(p, st);
+  }
+}
+}  // namespace mvgeo
+
+extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int H, int W, double scale_x, double scale_y,
+                                int apply_sigmoid, const float* kp_target, float sigma, float weight, int32_t* idx,
+                                float* peak, float* score, float* kp_hard, float* partial, float* loss, void* stream) {
+  if (n_maps < 0 || H <= 0 || W <= 0 || !(sigma > 0.f)) return MVGEO_EINVAL;
+  if ((int64_t)H * W > (int64_t)1 << 30 || n_maps > (int64_t)0x7fffffff) return MVGEO_EINVAL;
+  if (dtype != MVGEO_F32 && dtype != MVGEO_BF16 && dtype != MVGEO_F16) return MVGEO_EINVAL;
+  if (n_maps == 0) return MVGEO_OK;
+  if (!maps || !kp_target || !partial || !loss) return MVGEO_ENULL;
+  const int esize = dtype == MVGEO_F32 ? 4 : 2;
+  // the fused pass is the streaming kernel only: 16-byte aligned maps whose rows hold whole 16-byte chunks
+  if ((reinterpret_cast<uintptr_t>(maps) & 15) || (W * esize) % 16 != 0) return MVGEO_EUNSUPPORTED;
+  DecodeParams p = {};
+  p.view_base[0] = maps;
+  p.n_views = 1;
+  p.k_per_view = 1;
+  p.n_maps = n_maps;
+  p.map_bytes = (int64_t)H * W * esize;
+  p.H = H;
+  p.W = W;
+  p.chunks_per_map = (int)(p.map_bytes / 16);
+  p.scale_x = scale_x;
+  p.scale_y = scale_y;
+  p.apply_sigmoid = apply_sigmoid;
+  p.k_inner = 1;
+  p.out_stride = 1;
+  p.idx = idx;
+  p.peak = peak;
+  p.score = score;
+  p.kp_hard = kp_hard;
+  p.mse_kp = kp_target;
+  p.mse_k = kLog2e / (2.0f * sigma * sigma);
+  p.mse_partial = partial;
+  const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  switch (dtype) {
+    case MVGEO_F32: rc = launch_decode_mse<MVGEO_F32>(p, groups, st); break;
+    case MVGEO_BF16: rc = launch_decode_mse<MVGEO_BF16>(p, groups, st); break;
+    default: rc = launch_decode_mse<MVGEO_F16>(p, groups, st); break;
+  }
+  if (rc) return rc;
+  return finish_mse(partial, n_maps, (double)n_maps * H * W, weight, loss, st);
 }
 
 extern "C" int mvgeo_decode_views(const void* const* view_maps, int n_views, int dtype, int64_t B, int K, int H, int W,

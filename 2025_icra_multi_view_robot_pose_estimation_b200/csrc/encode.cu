@@ -281,6 +281,15 @@ static int launch_mse(const void* pred, const float* kp, int64_t n_maps, int H, 
   return MVGEO_OK;
 }
 
+// loss[0] = weight / N * sum(partial): shared by mvgeo_heatmap_mse and the fused decode + MSE pass (decode.cu)
+int finish_mse(const float* partial, int64_t n_maps, double N, float weight, float* loss, cudaStream_t st) {
+  int rc = launch_sum(partial, n_maps, loss, st);
+  if (rc) return rc;
+  scale_kernel<<<1, 1, 0, st>>>(loss, (float)((double)weight / N));
+  MVGEO_CHECK_LAUNCH();
+  return MVGEO_OK;
+}
+
 static int check_maps_args(int64_t n_maps, int H, int W, int dtype, float sigma) {
   if (n_maps < 0 || H <= 0 || W <= 0 || H + W > kEncMaxDim || !(sigma > 0.f)) return MVGEO_EINVAL;
   if (dtype != MVGEO_F32 && dtype != MVGEO_BF16 && dtype != MVGEO_F16) return MVGEO_EINVAL;
@@ -329,9 +338,5 @@ extern "C" int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, i
     default: rc = launch_mse<MVGEO_F16>(pred, kp, n_maps, H, W, k, gs, dloss, partial, grad, vec, st); break;
   }
   if (rc) return rc;
-  rc = launch_sum(partial, n_maps, loss, st);
-  if (rc) return rc;
-  scale_kernel<<<1, 1, 0, st>>>(loss, (float)((double)weight / N));
-  MVGEO_CHECK_LAUNCH();
-  return MVGEO_OK;
+  return finish_mse(partial, n_maps, N, weight, loss, st);
 }

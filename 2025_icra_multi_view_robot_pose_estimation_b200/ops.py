@@ -335,6 +335,46 @@ def pnp_refine(X: torch.Tensor, kp: torch.Tensor, cams, w: Optional[torch.Tensor
     return rvec, tvec, rms, status
 
 
+def pnp_solve(X: torch.Tensor, kp: torch.Tensor, cams, w: Optional[torch.Tensor] = None, *, min_weight: float = 0.0,
+              reproj_thresh: float = 8.0, max_iters: int = 30):
+    """Batched camera pose WITHOUT a prior per (frame, view): every key-point triplet is a P3P hypothesis,
+    consensus at `reproj_thresh` pixels, Levenberg-Marquardt on the inliers — the batched replacement of
+    cv2.solvePnPRansac(..., flags=cv2.SOLVEPNP_EPNP) in estimate_camera_pose (model/Fr5_model_train.ipynb:4735-4741).
+    Only the intrinsics / distortion of `cams` are used. Shapes as pnp_refine.
+    Returns rvec (B,V,3), tvec (B,V,3), rms (B,V), status (B,V) int32 (0 = refused: < 4 valid points or < 4
+    inliers, pose NaN), inliers (B,V) int32 bit mask."""
+    lib = _lib.load()
+    X = _need_cuda(X, "X", torch.float32)
+    kp = _need_cuda(kp, "kp", torch.float32)
+    dev = X.device
+    cams_t = cameras_to_device(cams, dev)
+    V = int(cams_t.shape[0])
+    if kp.dim() != 4 or kp.shape[1] != V or kp.shape[-1] != 2:
+        raise ValueError("kp must be (B, V, K, 2) with V matching the rig")
+    B, _, K, _ = kp.shape
+    if X.dim() == 3 and tuple(X.shape) == (B, K, 3):
+        per_view = 0
+    elif X.dim() == 4 and tuple(X.shape) == (B, V, K, 3):
+        per_view = 1
+    else:
+        raise ValueError("X must be (B,K,3) or (B,V,K,3)")
+    if w is not None:
+        w = _need_cuda(w, "w", torch.float32)
+        if tuple(w.shape) != (B, V, K):
+            raise ValueError("w must be (B, V, K)")
+    rvec = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
+    tvec = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
+    rms = torch.empty((B, V), dtype=torch.float32, device=dev)
+    status = torch.empty((B, V), dtype=torch.int32, device=dev)
+    inliers = torch.empty((B, V), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvgeo_pnp_solve(X.data_ptr(), per_view, kp.data_ptr(), _ptr(w), cams_t.data_ptr(), B, V, K,
+                                       float(min_weight), float(reproj_thresh), int(max_iters), rvec.data_ptr(),
+                                       tvec.data_ptr(), rms.data_ptr(), status.data_ptr(), inliers.data_ptr(),
+                                       _stream(dev)), "mvgeo_pnp_solve")
+    return rvec, tvec, rms, status, inliers
+
+
 # --------------------------------------------------------------- GT encoder and heat-map MSE
 def encode_gaussian(kp: torch.Tensor, heatmap_size, sigma: float, dtype=torch.float32) -> torch.Tensor:
     """Batched create_gt_heatmap (model/MvRoPose_FR3.py:65-73): kp (..., 2) in MAP pixels ->
@@ -392,6 +432,59 @@ def heatmap_mse_loss(pred: torch.Tensor, kp: torch.Tensor, sigma: float, weight:
     if tuple(kp.shape) != tuple(pred.shape[:-2]) + (2,):
         raise ValueError("kp must be pred.shape[:-2] + (2,)")
     return _HeatmapMSE.apply(pred, kp, sigma, weight)
+
+
+class _DecodeMSE(torch.autograd.Function):
+    """Forward: ONE read of the prediction gives the loss and the hard decode (mvgeo_decode_mse). Backward: the
+    gradient pass of mvgeo_heatmap_mse (reads the prediction, writes the gradient, upstream scalar applied on the device)."""
+
+    @staticmethod
+    def forward(ctx, pred, kp, sigma, weight, sx, sy, apply_sigmoid):
+        lib = _lib.load()
+        dev = pred.device
+        H, W = int(pred.shape[-2]), int(pred.shape[-1])
+        lead = tuple(pred.shape[:-2])
+        n_maps = pred.numel() // (H * W)
+        idx = torch.empty(lead, dtype=torch.int32, device=dev)
+        peak = torch.empty(lead, dtype=torch.float32, device=dev)
+        score = torch.empty(lead, dtype=torch.float32, device=dev)
+        kp_hard = torch.empty(lead + (2,), dtype=torch.float32, device=dev)
+        partial = torch.empty((n_maps,), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvgeo_decode_mse(pred.data_ptr(), _DTYPES[pred.dtype], n_maps, H, W, sx, sy, int(bool(apply_sigmoid)),
+                                            kp.data_ptr(), float(sigma), float(weight), idx.data_ptr(), peak.data_ptr(),
+                                            score.data_ptr(), kp_hard.data_ptr(), partial.data_ptr(), loss.data_ptr(),
+                                            _stream(dev)), "mvgeo_decode_mse")
+        ctx.save_for_backward(pred, kp)
+        ctx.sigma, ctx.weight = float(sigma), float(weight)
+        ctx.mark_non_differentiable(idx, peak, score, kp_hard)
+        return loss, idx, peak, score, kp_hard
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        pred, kp = ctx.saved_tensors
+        grad = torch.empty_like(pred)
+        _HeatmapMSE._call(pred, kp, ctx.sigma, ctx.weight, g.to(dtype=torch.float32).contiguous(), grad)
+        return grad, None, None, None, None, None, None
+
+
+def decode_and_mse(pred: torch.Tensor, kp_target: torch.Tensor, sigma: float, weight: float = 1.0, image_size=None,
+                   apply_sigmoid: bool = False):
+    """One-read training step: heat-map MSE loss against Gaussian targets centred at
+    kp_target (map pixels) AND the hard decode of the same prediction, the maps read from HBM once.
+    Returns (loss [differentiable w.r.t. pred], DecodeResult with kp_soft = kp_hard).
+    Falls back to nothing: maps the fused kernel cannot take raise ValueError (use heatmap_mse_loss + decode_heatmaps)."""
+    pred = _need_cuda(pred, "pred")
+    kp_target = _need_cuda(kp_target, "kp_target", torch.float32)
+    if pred.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {pred.dtype}")
+    if tuple(kp_target.shape) != tuple(pred.shape[:-2]) + (2,):
+        raise ValueError("kp_target must be pred.shape[:-2] + (2,)")
+    H, W = int(pred.shape[-2]), int(pred.shape[-1])
+    sx, sy = _scales(image_size, H, W)
+    loss, idx, peak, score, kp_hard = _DecodeMSE.apply(pred, kp_target, sigma, weight, sx, sy, apply_sigmoid)
+    return loss, DecodeResult(idx, peak, score, kp_hard, kp_hard)
 
 
 # --------------------------------------------------------------------------- fused pipeline

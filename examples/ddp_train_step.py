@@ -47,8 +47,10 @@ class Heads(nn.Module):
     def __init__(self, C, K, J, V, width):
         super().__init__()
         self.V = V
+        # (the 4x up-sampling acts on the K heat-map channels: torch's bilinear backward launches one grid row per
+        # (image, channel) and refuses 450 x ~1000 of them)
         self.kpt = nn.Sequential(nn.Conv2d(C, width, 3, padding=1), nn.GELU(), nn.Conv2d(width, width, 3, padding=1), nn.GELU(),
-                                 nn.Upsample(scale_factor=4, mode="bilinear"), nn.Conv2d(width, K, 3, padding=1))
+                                 nn.Conv2d(width, K, 3, padding=1), nn.Upsample(scale_factor=4, mode="bilinear"))
         self.ang = nn.Sequential(nn.Linear(C * V, 4 * width), nn.GELU(), nn.Linear(4 * width, 4 * width), nn.GELU(),
                                  nn.Linear(4 * width, J))
 

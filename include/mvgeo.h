@@ -250,6 +250,22 @@ int mvgeo_pnp_refine(const float* X, int x_per_view, const float* kp, const floa
                      const mvgeo_camera* cams, int64_t B, int V, int K, float min_weight, int max_iters,
                      float* rvec, float* tvec, float* rms, int32_t* status, void* stream);
 
+/* Pose WITHOUT a prior: replaces cv2.solvePnPRansac(object_points, image_points, camera_matrix, dist_coeffs,
+ * flags=cv2.SOLVEPNP_EPNP) inside estimate_camera_pose (model/Fr5_model_train.ipynb:4735-4741,
+ * model/Franka_research3_model_train.ipynb:3690-3692). K <= 16 key-points make random sampling pointless:
+ * every point triplet is a P3P hypothesis, scored on all valid points (inliers within reproj_thresh pixels —
+ * OpenCV's default reprojectionError is 8 — then the inliers' squared error); the best one is refined by the
+ * Levenberg-Marquardt of mvgeo_pnp_refine on its inliers. cams[v] supplies intrinsics and distortion only.
+ * Refusals of the reference are kept: fewer than 4 valid points (:4728) or fewer than 4 inliers (:4743)
+ * give status 0 and a NaN pose (the reference returns None).
+ *   arguments as mvgeo_pnp_refine, plus
+ *   inliers [B, V] i32  bit k set: key-point k is an inlier of the returned pose      (nullable)
+ */
+int mvgeo_pnp_solve(const float* X, int x_per_view, const float* kp, const float* w,
+                    const mvgeo_camera* cams, int64_t B, int V, int K, float min_weight, float reproj_thresh,
+                    int max_iters, float* rvec, float* tvec, float* rms, int32_t* status, int32_t* inliers,
+                    void* stream);
+
 /* -------------------------------------------------- GT belief-map encoder
  * Replaces create_gt_heatmap (model/MvRoPose_FR3.py:65-73, model/DREAM_Train.py:60-69):
  * exp(-((x-cx)^2+(y-cy)^2)/(2 sigma^2)), values below eps(double)*max set to 0.
@@ -269,6 +285,20 @@ int mvgeo_encode_gaussian(const float* kp, int64_t n_maps, int H, int W, float s
 int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, int64_t n_maps, int H, int W,
                       float sigma, float weight, const float* dloss, float* partial, float* loss, void* grad,
                       void* stream);
+
+/* ---------------------------------- one-read training step: decode + heat-map MSE in ONE pass
+ * mvgeo_decode (hard arg-max: idx, peak, score, kp_hard) and the forward of mvgeo_heatmap_mse over the SAME
+ * predicted maps, which are read from HBM once (the reference reads them for nn.MSELoss,
+ * model/MvRoPose_FR3.py:846-847, and again when decoding for evaluation, :299-304).
+ *   kp_target [n_maps, 2] f32 target centres in MAP pixels; partial [n_maps] f32 scratch; loss [1] f32
+ * Needs 16-byte aligned maps whose rows hold whole 16-byte chunks and (W + H) * 4 bytes * groups of shared
+ * memory <= 16 KB; otherwise MVGEO_EUNSUPPORTED (call the two stand-alone entry points). The gradient pass is
+ * mvgeo_heatmap_mse with `grad` (it reads the prediction and writes the gradient).
+ */
+int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int H, int W, double scale_x, double scale_y,
+                     int apply_sigmoid, const float* kp_target, float sigma, float weight,
+                     int32_t* idx, float* peak, float* score, float* kp_hard,
+                     float* partial, float* loss, void* stream);
 
 /* -------------------------------------------------------- fused pipeline
  * decode -> triangulate -> FK -> reprojection consistency, one stream, no host sync: two launches

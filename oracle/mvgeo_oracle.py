@@ -589,6 +589,103 @@ def pnp_refine(X, kp, K, dist, R0, t0, w=None, min_weight: float = 0.0, max_iter
     return rvec_from_matrix(R), t, math.sqrt(cost / n), status
 
 
+def p3p_poses(f, P):
+    """Perspective-3-point (Grunert's formulation, reviewed in Haralick et al. 1994): unit bearings f (3,3)
+    and world points P (3,3) -> list of (R, t) with s_i f_i = R P_i + t, all real solutions with positive
+    depths. With s2 = u s1, s3 = v s1 the three law-of-cosines equations reduce to a quartic in v whose
+    coefficients are formed here by polynomial arithmetic (no hand-expanded coefficient table)."""
+    f = np.asarray(f, dtype=np.float64)
+    P = np.asarray(P, dtype=np.float64)
+    a2, b2, c2 = np.sum((P[1] - P[2]) ** 2), np.sum((P[0] - P[2]) ** 2), np.sum((P[0] - P[1]) ** 2)
+    if min(a2, b2, c2) < 1e-18:
+        return []
+    ca, cb, cg = float(f[1] @ f[2]), float(f[0] @ f[2]), float(f[0] @ f[1])
+    k = (a2 - c2) / b2
+    # u = N(v) / D(v) from (eq.1 - eq.3 scaled by eq.2)
+    N = np.array([k - 1.0, -2.0 * k * cb, 1.0 + k])          # v^2, v^1, v^0
+    D = np.array([-2.0 * ca, 2.0 * cg])                       # v^1, v^0
+    q = np.array([1.0, -2.0 * cb, 1.0])                       # 1 + v^2 - 2 v cos(beta)
+    DD = np.polymul(D, D)
+    quartic = np.polyadd(np.polyadd(np.polyadd(DD, np.polymul(N, N)), -2.0 * cg * np.polymul(N, D)),
+                         -(c2 / b2) * np.polymul(q, DD))
+    out = []
+    for v in np.roots(quartic):
+        if abs(v.imag) > 1e-7 * max(1.0, abs(v.real)) or v.real <= 0:
+            continue
+        v = float(v.real)
+        den = 2.0 * (cg - v * ca)
+        if abs(den) < 1e-12:
+            continue
+        u = ((k - 1.0) * v * v - 2.0 * k * cb * v + 1.0 + k) / den
+        w = 1.0 + v * v - 2.0 * v * cb
+        if u <= 0 or w <= 0:
+            continue
+        s1 = math.sqrt(b2 / w)
+        Q = np.stack([s1 * f[0], u * s1 * f[1], v * s1 * f[2]])
+
+        def frame(A):
+            e1 = A[1] - A[0]
+            e1 = e1 / np.linalg.norm(e1)
+            e3 = np.cross(e1, A[2] - A[0])
+            n3 = np.linalg.norm(e3)
+            if n3 < 1e-12:
+                return None
+            e3 = e3 / n3
+            return np.stack([e1, np.cross(e3, e1), e3], axis=1)   # columns
+        Fp, Fq = frame(P), frame(Q)
+        if Fp is None or Fq is None:
+            continue
+        R = Fq @ Fp.T
+        out.append((R, Q[0] - R @ P[0]))
+    return out
+
+
+def pnp_solve(X, kp, K, dist=None, w=None, min_weight: float = 0.0, reproj_thresh: float = 8.0, max_iters: int = 30):
+    """Camera pose WITHOUT a prior — the specification of mvgeo_pnp_solve, which replaces
+    cv2.solvePnPRansac(obj, img, K, dist, flags=SOLVEPNP_EPNP) in estimate_camera_pose
+    (model/Fr5_model_train.ipynb:4707-4753; defaults: reprojectionError 8 px). K <= 9 key-points make random
+    sampling pointless: EVERY point triplet is a hypothesis (P3P, up to 4 poses each), every hypothesis is
+    scored on all valid points (inlier count at `reproj_thresh`, then squared error of the inliers), and the
+    winner is refined by Levenberg-Marquardt on its inliers (pnp_refine above: the cost
+    cv2.solvePnP(SOLVEPNP_ITERATIVE) minimises). Fewer than 4 valid points, no hypothesis, or fewer than 4
+    inliers -> None (the reference's refusals, :4728 and `num_inliers >= 4`).
+    Returns (rvec, tvec, inlier_mask (K,), rms_px, status) or None."""
+    import itertools
+
+    X = np.asarray(X, dtype=np.float64)
+    kp = np.asarray(kp, dtype=np.float64)
+    Kn = len(X)
+    dist = np.zeros(5) if dist is None else np.asarray(dist, dtype=np.float64).reshape(-1)[:5]
+    ok = np.isfinite(kp).all(axis=1) & np.isfinite(X).all(axis=1)
+    if w is not None:
+        ok &= np.asarray(w, dtype=np.float64) >= min_weight
+    idx = np.flatnonzero(ok)
+    if len(idx) < 4:
+        return None
+    und = undistort_points(kp, K, dist)                      # ideal pinhole pixels
+    K = np.asarray(K, dtype=np.float64)
+    xn = np.stack([(und[:, 0] - K[0, 2]) / K[0, 0], (und[:, 1] - K[1, 2]) / K[1, 1], np.ones(Kn)], axis=1)
+    f = xn / np.linalg.norm(xn, axis=1, keepdims=True)
+    best, best_key = None, None
+    for tri in itertools.combinations(idx, 3):
+        for R, t in p3p_poses(f[list(tri)], X[list(tri)]):
+            Xc = X[idx] @ R.T + t
+            if np.any(Xc[:, 2] <= 1e-9):
+                continue                                      # a valid point behind the camera
+            e2 = np.sum((project_points(X[idx], R, t, K, dist) - kp[idx]) ** 2, axis=1)
+            inl = e2 < reproj_thresh ** 2
+            key = (int(inl.sum()), -float(e2[inl].sum()))
+            if best_key is None or key > best_key:
+                best_key, best = key, (R, t, inl)
+    if best is None or best_key[0] < 4:
+        return None
+    R, t, inl = best
+    mask = np.zeros(Kn, dtype=bool)
+    mask[idx[inl]] = True
+    rvec, tvec, rms, status = pnp_refine(X, kp, K, dist, R, t, mask.astype(np.float64), 0.5, max_iters)
+    return rvec, tvec, mask, rms, status
+
+
 def undistort_points(kp, K, dist, iters: int = 5) -> np.ndarray:
     """cv2.undistortPoints(kp, K, dist, P=K): OpenCV's fixed-point inversion of the Brown-Conrady
     model (5 iterations by default), float64. kp (...,2) pixels -> (...,2) pixels."""

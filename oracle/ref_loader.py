@@ -6,9 +6,10 @@ GPU box, so nothing under `-m gpu`, smoke() or bench.py may call this. It is use
 tests/golden/make_golden.py (to freeze golden vectors) and by CPU tests that skip when the
 checkout is absent.
 
-The reference has no package: functions live in scripts and notebook cells. Scripts are
-imported with stubbed third-party modules (timm, kornia, matplotlib, wandb, pyzed are absent
-here); notebook cells are exec'd into a namespace holding only what they need.
+The reference has no package: functions live in scripts and notebook cells. Nothing is imported or
+run wholesale: only the `def` blocks of the named functions are extracted from a script / notebook cell
+and exec'd into a namespace holding exactly the modules they need (numpy, math, cv2, scipy Rotation,
+torch), so no module-level reference code ever executes.
 """
 from __future__ import annotations
 
@@ -25,51 +26,6 @@ REF_ROOT = os.environ.get("MVGEO_REFERENCE_ROOT", "/root/reference")
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "model", "MvRoPose_FR3.py"))
-
-
-def _stub(name: str):
-    if name in sys.modules:
-        return
-    try:
-        importlib.import_module(name)
-        return
-    except Exception:
-        pass
-    m = types.ModuleType(name)
-    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
-    m.__path__ = []
-
-    class _Anything:
-        def __init__(self, *a, **k):
-            pass
-
-        def __call__(self, *a, **k):
-            return _Anything()
-
-        def __getattr__(self, item):
-            return _Anything()
-
-    m.__getattr__ = lambda item: _Anything()  # type: ignore[attr-defined]
-    sys.modules[name] = m
-
-
-def load_script(rel_path: str, modname: str):
-    """Import a reference script (its main() is guarded by __name__ == '__main__')."""
-    import transformers  # noqa: F401  (must be imported before timm is stubbed)
-    from transformers import AutoImageProcessor, AutoModel  # noqa: F401
-
-    for name in ("timm", "kornia", "kornia.augmentation", "matplotlib", "matplotlib.pyplot", "wandb",
-                 "pyzed", "pyzed.sl", "seaborn"):
-        _stub(name)
-    path = os.path.join(REF_ROOT, rel_path)
-    spec = importlib.util.spec_from_file_location(modname, path)
-    mod = importlib.util.module_from_spec(spec)
-    cwd = os.getcwd()
-    try:
-        spec.loader.exec_module(mod)
-    finally:
-        os.chdir(cwd)
-    return mod
 
 
 def _cell_source(nb_rel: str, cell: int) -> str:

@@ -1090,3 +1090,153 @@ def test_host_pipeline_keeps_the_callers_device(mv):
     if torch.cuda.device_count() == 1:
         full = mv.pipeline(maps, P, chain, q, rig, Rv, image_size=rig.image_size)
         assert torch.equal(out["idx"], full["idx"].cpu()) and torch.equal(out["X_tri"], full["X_tri"].cpu())
+
+
+def _rot_angle(r1, r2):
+    return float(np.linalg.norm(O.rvec_from_matrix(O.rodrigues(r1) @ O.rodrigues(r2).T)))
+
+
+@pytest.mark.parametrize("robot", ["fr3", "fr5"])
+def test_pnp_solve_without_prior_vs_oracle_and_cv2(mv, robot):
+    """mvgeo_pnp_solve (every-triplet P3P consensus + LM) against its float64 restatement and against OpenCV:
+    the inlier set of cv2.solvePnPRansac(..., SOLVEPNP_EPNP) (the call it replaces, Fr5_model_train.ipynb:4735) and
+    the pose of cv2.solvePnP(SOLVEPNP_ITERATIVE) on those inliers, within 1e-3 rad / 1 mm. Real robot geometry
+    (FK points incl. FR3's coincident joints), ZED intrinsics with distortion, 0.3 px noise, 0-2 gross outliers."""
+    import cv2
+    rng = np.random.default_rng(11)
+    chain, q, _ = _chain_and_q(mv, robot)
+    B = 24
+    q = torch.from_numpy(np.asarray(q, dtype=np.float32)[:B]).to(DEV)
+    Xb = _to_np32(mv.forward_kinematics(chain, q))[:, 0]                  # (B,K,3) base frame
+    K = Xb.shape[1]
+    rig = mv.CameraRig.synthetic_ring(2, distortion=True)
+    kp = np.stack([O.project_points(Xb, rig.R[v], rig.t[v], rig.K[v], rig.dist[v]) for v in range(2)], axis=1)
+    kp = (kp + rng.normal(0, 0.3, kp.shape)).astype(np.float32)
+    n_out = np.zeros((B, 2), dtype=int)
+    for b in range(B):
+        for v in range(2):
+            n_out[b, v] = (b + v) % 3
+            for k in rng.choice(K, n_out[b, v], replace=False):
+                kp[b, v, k] += rng.uniform(40, 150, 2) * rng.choice([-1, 1], 2)
+    rv, tv, rms, st, inl = mv.pnp_solve(torch.from_numpy(Xb).to(DEV), torch.from_numpy(kp).to(DEV), rig)
+    rv, tv, st, inl = _to_np32(rv), _to_np32(tv), st.cpu().numpy(), inl.cpu().numpy()
+    worst = [0.0, 0.0, 0.0, 0.0]
+    n_cv = n_same = 0
+
+    def cost(rvec_, tvec_, b, v, m):
+        e = O.project_points(Xb[b][m], O.rodrigues(rvec_), np.asarray(tvec_, dtype=np.float64).reshape(3), rig.K[v], rig.dist[v]) - kp[b, v][m]
+        return float(np.sum(e * e))
+
+    for b in range(B):
+        for v in range(2):
+            ref = O.pnp_solve(Xb[b], kp[b, v], rig.K[v], rig.dist[v])
+            assert ref is not None and (st[b, v] & 3) == 3, (b, v, st[b, v])
+            mask = np.array([(inl[b, v] >> k) & 1 for k in range(K)], dtype=bool)
+            np.testing.assert_array_equal(mask, ref[2])
+            worst[0] = max(worst[0], _rot_angle(rv[b, v], ref[0]))
+            worst[1] = max(worst[1], float(np.linalg.norm(tv[b, v] - ref[1])))
+            ok, r0, t0, cvin = cv2.solvePnPRansac(Xb[b].astype(np.float64), kp[b, v].astype(np.float64), rig.K[v], rig.dist[v],
+                                                  flags=cv2.SOLVEPNP_EPNP)
+            if not ok or cvin is None or len(cvin) < 4:
+                continue
+            cvmask = np.zeros(K, dtype=bool)
+            cvmask[cvin.reshape(-1)] = True
+            if not np.array_equal(cvmask, mask):
+                continue                                   # RANSAC is random: compare poses only on equal consensus sets
+            n_cv += 1
+            _, r1, t1 = cv2.solvePnP(Xb[b][cvmask].astype(np.float64), kp[b, v][cvmask].astype(np.float64), rig.K[v], rig.dist[v],
+                                     rvec=r0.copy(), tvec=t0.copy(), useExtrinsicGuess=True, flags=cv2.SOLVEPNP_ITERATIVE)
+            # never a worse minimum of the reprojection error than OpenCV's (FR3's coincident / near-planar key-points
+            # give cv2's EPnP start a mirror pose now and then: ours scores every P3P hypothesis and keeps the best)
+            c_ours, c_cv = cost(rv[b, v], tv[b, v], b, v, cvmask), cost(r1.reshape(3), t1.reshape(3), b, v, cvmask)
+            assert c_ours <= c_cv * (1 + 1e-4) + 1e-6, (b, v, c_ours, c_cv)
+            dr, dt = _rot_angle(rv[b, v], r1.reshape(3)), float(np.linalg.norm(tv[b, v] - t1.reshape(3)))
+            if c_cv <= c_ours * (1 + 1e-3) + 1e-6:         # same minimum: same pose
+                n_same += 1
+                worst[2], worst[3] = max(worst[2], dr), max(worst[3], dt)
+    print(f"pnp_solve {robot}: vs oracle {worst[0]:.1e} rad {worst[1]:.1e} m; equal consensus set as cv2.solvePnPRansac in {n_cv} of "
+          f"{2 * B} cases, same minimum as cv2's LM in {n_same}: {worst[2]:.1e} rad {worst[3]:.1e} m")
+    assert worst[0] < 1e-4 and worst[1] < 1e-4
+    assert n_cv >= B and n_same >= 0.9 * n_cv and worst[2] < 1e-3 and worst[3] < 1e-3
+    # the true pose is recovered to the accuracy 0.3 px of noise allows
+    for v in range(2):
+        assert max(_rot_angle(rv[b, v], O.rvec_from_matrix(rig.R[v])) for b in range(B)) < 0.05
+    # refusals: fewer than 4 confident points -> status 0 and a NaN pose
+    w = np.ones((B, 2, K), dtype=np.float32)
+    w[:, :, 3:] = 0.0
+    rv2, tv2, _, st2, inl2 = mv.pnp_solve(torch.from_numpy(Xb).to(DEV), torch.from_numpy(kp).to(DEV), rig,
+                                          torch.from_numpy(w).to(DEV), min_weight=0.5)
+    assert (st2 == 0).all() and torch.isnan(rv2).all() and torch.isnan(tv2).all() and (inl2 == 0).all()
+
+
+def test_estimate_camera_pose_shims(mv):
+    """compat.fr5 / compat.fr3 estimate_camera_pose: same returns as the reference function
+    (model/Fr5_model_train.ipynb:4707-4753, Franka_research3_model_train.ipynb:3667-3708): (rvec (3,1), tvec (3,1),
+    object points, image points) or (None, None, ...) below 4 confident points / outside the 0.5-5 m gate."""
+    import cv2
+    from mvgeo.compat import fr3, fr5
+    rng = np.random.default_rng(8)
+    size = (1080, 1920)
+    Kc = np.array([[1066.51, 0, 989.51], [0, 1066.89, 578.779], [0, 0, 1.0]])
+    dist = np.array([-0.0056, -0.0461, 1.3e-4, 3.1e-4, 0.0148])
+    for ns, robot, ang, view in ((fr5, "fr5", [-60.66, -95.86, 117.44, -111.57, -90.0, 29.34], "top"),
+                                 (fr3, "fr3", [0.648, -0.108, 0.21, -1.92, 0.886, 3.10, -2.39], "view1")):
+        X = ns.angle_to_joint_coordinate(ang, view)
+        R = O.rodrigues([1.9, 0.3, -0.2])
+        t = np.array([0.1, 0.2, 1.8])
+        uv = O.project_points(X, R, t, Kc, dist)
+        assert (uv[:, 0] > 0).all() and (uv[:, 0] < size[1]).all() and (uv[:, 1] > 0).all() and (uv[:, 1] < size[0]).all()
+        hs = (270, 480)                                                     # 4 image px per cell: every point is an inlier at 8 px
+        kp_map = torch.tensor(uv * [hs[1] / size[1], hs[0] / size[0]], dtype=torch.float32, device=DEV)
+        hm = mv.encode_gaussian(kp_map, hs, 2.0) * 6.0 - 3.0                # logits: sigmoid(peak) ~ 0.95, background ~ 0.05
+        rv, tv, obj, img = ns.estimate_camera_pose(torch.tensor(ang), hm.cpu(), Kc, dist, view, size, confidence_threshold=0.5)
+        assert rv.shape == (3, 1) and tv.shape == (3, 1) and rv.dtype == np.float64 and obj.shape == (len(X), 3) and img.shape == (len(X), 2)
+        np.testing.assert_allclose(obj, X, atol=1e-6)
+        # the reference's own path on the same decoded key-points
+        ok, r0, t0, inl = cv2.solvePnPRansac(obj.astype(np.float64), img.astype(np.float64), Kc, dist, flags=cv2.SOLVEPNP_EPNP)
+        assert ok and len(inl) == len(X)
+        _, r1, t1 = cv2.solvePnP(obj[inl.reshape(-1)].astype(np.float64), img[inl.reshape(-1)].astype(np.float64), Kc, dist,
+                                 rvec=r0, tvec=t0, useExtrinsicGuess=True, flags=cv2.SOLVEPNP_ITERATIVE)
+        assert _rot_angle(rv.reshape(3), r1.reshape(3)) < 1e-3 and np.linalg.norm(tv - t1) < 1e-3
+        assert _rot_angle(rv.reshape(3), O.rvec_from_matrix(R)) < 0.05     # key-points are quantised to 4-px map cells
+        # fewer than 4 confident key-points: refused like the reference (:4728)
+        hm_low = hm.clone()
+        hm_low[3:] = -3.0
+        rv, tv, obj2, img2 = ns.estimate_camera_pose(torch.tensor(ang), hm_low.cpu(), Kc, dist, view, size, confidence_threshold=0.5)
+        assert rv is None and tv is None and obj2.shape == obj.shape and img2.shape == img.shape
+    # FR3 variant: implausible distance (|t| > 5 m) is rejected, the Fr5 variant has no gate
+    ang = [0.648, -0.108, 0.21, -1.92, 0.886, 3.10, -2.39]
+    X = fr3.angle_to_joint_coordinate(ang, "view1")
+    uv = O.project_points(X, O.rodrigues([1.9, 0.3, -0.2]), np.array([0.2, 0.1, 7.0]), Kc, dist)
+    hm = mv.encode_gaussian(torch.tensor(uv * [480 / size[1], 270 / size[0]], dtype=torch.float32, device=DEV), (270, 480), 1.0) * 6.0 - 3.0
+    assert fr3.estimate_camera_pose(torch.tensor(ang), hm.cpu(), Kc, dist, "view1", size, 0.5)[0] is None
+
+
+@pytest.mark.parametrize("dtype,HW", [(torch.float32, (128, 128)), (torch.bfloat16, (128, 128)), (torch.bfloat16, (240, 320)),
+                                      (torch.float16, (120, 160)), (torch.bfloat16, (480, 640))])
+def test_decode_and_mse_one_read(mv, dtype, HW):
+    """mvgeo_decode_mse: the training step's heat-map MSE (nn.MSELoss vs Gaussian targets, model/MvRoPose_FR3.py:846-847)
+    and the hard decode of the same prediction in ONE pass: loss against the float64 restatement (1e-5 relative),
+    arg-max bit-exact, gradient equal to the stand-alone loss kernel's."""
+    rng = np.random.default_rng(19)
+    H, W = HW
+    n = 37
+    a, c = _blob_maps(rng, n, H, W, sigma=4.0, noise=0.05)
+    tgt = (c + rng.normal(0, 2.0, c.shape)).astype(np.float32)
+    tgt[3] = np.nan                                            # missing key-point: all-zero target
+    t, seen = _as_dtype(a, dtype)
+    kp = torch.from_numpy(tgt).to(DEV)
+    tq = t.clone().requires_grad_(True)
+    loss, dec = mv.decode_and_mse(tq, kp, sigma=5.0, weight=1e4, image_size=(1200, 1920), apply_sigmoid=True)
+    ref_loss, ref_grad = O.heatmap_mse(seen, tgt, 5.0, 1e4)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss), (float(loss), ref_loss)
+    d = O.decode(seen, 1920 / W, 1200 / H, "none", apply_sigmoid=True)
+    np.testing.assert_array_equal(dec.idx.cpu().numpy(), d["idx"])
+    np.testing.assert_array_equal(_to_np32(dec.kp_hard), d["kp_hard"])
+    np.testing.assert_allclose(_to_np32(dec.score), d["score"], rtol=2e-6)
+    (loss * 0.5).backward()
+    t2 = t.clone().requires_grad_(True)
+    (mv.heatmap_mse_loss(t2, kp, 5.0, 1e4) * 0.5).backward()
+    assert torch.equal(tq.grad, t2.grad)
+    l2 = mv.heatmap_mse_loss(t, kp, 5.0, 1e4)
+    assert abs(float(loss) - float(l2)) <= 2e-6 * abs(float(l2))

@@ -294,3 +294,31 @@ int main(int argc, char** argv) {
     assert run.stdout.startswith("100 pointer is not aligned")
     assert f"sizeof(mvgeo_chain)={ctypes.sizeof(mv._lib.ChainStruct)} " in run.stdout  # ctypes mirror == C layout
     assert "sizeof(mvgeo_camera)=96 " in run.stdout and f"sizeof(mvgeo_pipeline_out)={ctypes.sizeof(mv._lib.PipelineOut)}" in run.stdout
+
+
+def test_numa_binding_helper_is_safe_without_a_gpu(mv):
+    """sharding.bind_to_gpu_numa never raises: unknown topology (no NVML / no GPU) returns None and leaves the
+    affinity untouched."""
+    before = os.sched_getaffinity(0)
+    r = mv.sharding.bind_to_gpu_numa(0)
+    assert r is None or set(r) <= set(before)
+    if r is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
+    assert isinstance(mv.sharding.gpu_local_cpus(0), list)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(mv):
+    lib = mv._lib.load()
+    z = ctypes.c_void_p(0)
+    views = (ctypes.c_void_p * 2)(None, None)
+    assert lib.mvgeo_decode_views(views, 0, 0, 4, 8, 8, 8, 1.0, 1.0, 0, 1.0, 0, 0, z, z, z, z, z, z) == -1          # no views
+    assert lib.mvgeo_decode_views(views, 2, 0, 4, 8, 8, 8, 1.0, 1.0, 0, 1.0, 0, 0, z, z, z, z, z, z) == -2          # NULL view
+    assert lib.mvgeo_decode_views(views, 2, 0, 0, 8, 8, 8, 1.0, 1.0, 0, 1.0, 0, 0, z, z, z, z, z, z) == 0           # empty
+    assert lib.mvgeo_decode_mse(z, 0, 4, 8, 8, 1.0, 1.0, 0, z, 0.0, 1.0, z, z, z, z, z, z, z) == -1                 # sigma <= 0
+    assert lib.mvgeo_decode_mse(z, 0, 4, 8, 8, 1.0, 1.0, 0, z, 2.0, 1.0, z, z, z, z, z, z, z) == -2                 # NULL maps
+    assert lib.mvgeo_pnp_solve(z, 0, z, z, z, 4, 2, 17, 0.0, 8.0, 10, z, z, z, z, z, z) == -1                       # K > 16
+    assert lib.mvgeo_pnp_solve(z, 0, z, z, z, 4, 2, 8, 0.0, 0.0, 10, z, z, z, z, z, z) == -1                        # threshold <= 0
+    assert lib.mvgeo_pnp_solve(z, 0, z, z, z, 4, 2, 8, 0.0, 8.0, 10, z, z, z, z, z, z) == -2
+    assert lib.mvgeo_pnp_solve(z, 0, z, z, z, 0, 2, 8, 0.0, 8.0, 10, z, z, z, z, z, z) == 0

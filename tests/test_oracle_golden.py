@@ -351,3 +351,51 @@ def test_average_quaternion_matches_reference_function():
     ref = ns["average_quaternion"](q)
     got = O.average_quaternion(q)
     assert abs(abs(ref @ got) - 1.0) < 1e-12
+
+
+def test_pnp_solve_oracle_p3p_consensus_vs_cv2():
+    """The specification of mvgeo_pnp_solve (every-triplet P3P consensus + LM) pinned against OpenCV: P3P returns the
+    true pose among its solutions; with 0-2 gross outliers of 8 points the consensus set is exactly the clean points and
+    the refined pose equals cv2.solvePnP(SOLVEPNP_ITERATIVE) on them; cv2.solvePnPRansac(SOLVEPNP_EPNP) — the call being
+    replaced (model/Fr5_model_train.ipynb:4735-4741) — lands within its own (non-optimal, random) accuracy of it."""
+    import cv2
+
+    rng = np.random.default_rng(0)
+    K = np.array([[1066.5, 0, 989.5], [0, 1066.9, 578.8], [0, 0, 1.0]])
+    dist = np.array([-0.005, -0.046, 1e-4, 3e-4, 0.0148])
+    # P3P alone, noise-free: one of the solutions is the truth
+    for _ in range(20):
+        rv = rng.normal(size=3)
+        R, t = O.rodrigues(rv), np.array([0.1, -0.2, rng.uniform(1.0, 3.0)])
+        P = rng.uniform(-0.4, 0.4, size=(3, 3))
+        Xc = P @ R.T + t
+        f = Xc / np.linalg.norm(Xc, axis=1, keepdims=True)
+        sols = O.p3p_poses(f, P)
+        assert 1 <= len(sols) <= 4
+        assert min(np.abs(Rs - R).max() + np.abs(ts - t).max() for Rs, ts in sols) < 1e-7
+    worst_r = worst_t = 0.0
+    for trial in range(30):
+        rv = rng.normal(size=3)
+        rv *= rng.uniform(0.2, 2.5) / np.linalg.norm(rv)
+        R = O.rodrigues(rv)
+        X = rng.uniform(-0.4, 0.4, size=(8, 3))
+        t = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(1.0, 3.0)])
+        kp = O.project_points(X, R, t, K, dist) + rng.normal(0, 0.3, size=(8, 2))
+        out_idx = rng.choice(8, trial % 3, replace=False)
+        kp[out_idx] += rng.uniform(40, 120, size=(len(out_idx), 2)) * rng.choice([-1, 1], size=(len(out_idx), 2))
+        rvec, tvec, mask, rms, st = O.pnp_solve(X, kp, K, dist)
+        clean = np.ones(8, dtype=bool)
+        clean[out_idx] = False
+        np.testing.assert_array_equal(mask, clean)
+        assert st & 1 and rms < 1.0
+        _, r2, t2 = cv2.solvePnP(X[clean], kp[clean], K, dist, rvec=rv.reshape(3, 1).copy(), tvec=t.reshape(3, 1).copy(),
+                                 useExtrinsicGuess=True, flags=cv2.SOLVEPNP_ITERATIVE)
+        dR = O.rodrigues(rvec) @ O.rodrigues(r2.reshape(3)).T
+        worst_r = max(worst_r, float(np.linalg.norm(O.rvec_from_matrix(dR))))
+        worst_t = max(worst_t, float(np.linalg.norm(tvec - t2.reshape(3))))
+        ok, r3, t3, inl = cv2.solvePnPRansac(X, kp, K, dist, flags=cv2.SOLVEPNP_EPNP)
+        if ok:
+            assert np.linalg.norm(tvec - t3.reshape(3)) < 0.05
+    assert worst_r < 1e-6 and worst_t < 1e-6, (worst_r, worst_t)
+    # the reference's refusals: fewer than 4 confident points -> None
+    assert O.pnp_solve(X, kp, K, dist, w=np.array([1, 1, 1, 0, 0, 0, 0, 0.0]), min_weight=0.5) is None

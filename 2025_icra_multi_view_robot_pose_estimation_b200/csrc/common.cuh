@@ -109,6 +109,11 @@ __device__ __forceinline__ float lds32f(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ void sts32f(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }

@@ -30,7 +30,10 @@
 //   * V per-view base pointers (the reference's dict view -> (B,K,H,W), model/MvRoPose_FR3.py:625)
 //     are walked by ONE launch: map m = (b, v, k) is read from view v's tensor, results land in
 //     [B,V,K] order. No stack copy, no per-view launch.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <atomic>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -47,7 +50,7 @@ struct DecodeParams {
   int64_t n_maps;
   int64_t map_bytes;
   int H, W;
-  int chunks_per_map;  // vector kernel: H*W*sizeof / 16
+  int rows_per_map;    // streaming kernel: H*W*sizeof / 64 (64-byte runs per map)
   double scale_x, scale_y;
   float beta_log2e;  // beta * log2(e)
   float skip_delta;  // scalar kernel only: kSoftSkip / beta
@@ -287,22 +290,48 @@ __device__ __forceinline__ float ord_val(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Up to MVGEO_MAX_VIEWS TMA tensor maps, one per base pointer (kernel parameter, __grid_constant__): every
+// view's maps seen as a 2-D tensor [rows of 128 bytes][128 bytes].
+struct TensorMaps {
+  CUtensorMap m[MVGEO_MAX_VIEWS];
+};
+
+// 2-D tiled TMA load (SASS UTMALDG): box = [rows x 128 B] at row `row` into `dst`, bytes counted on `bar`.
+__device__ __forceinline__ void tma_load_rows(uint32_t dst_smem, const CUtensorMap* tm, int row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   dst_smem),
+               "l"(tm), "r"(0), "r"(row), "r"(bar)
+               : "memory");
+}
+
 // G independent consumer groups per CTA (8/G warps each, own ring, own mbarriers, own named
 // barrier, own map sequence): small maps use G > 1 so that one group's latency-bound epilogue
 // overlaps the other groups' streaming. Producer warp 8+g (one elected lane) feeds group g.
 // Grid = one resident wave; group (blockIdx.x, g) walks maps blockIdx.x*G + g, +gridDim.x*G, ...
+//
+// Tile = NT/2 rows of 128 bytes, loaded by ONE 2-D TMA tensor copy with the 128-byte swizzle: thread gt owns half
+// (gt & 1) of row gt >> 1, i.e. a RUN of 64 contiguous map bytes (32 bf16 / 16 f32 elements, inside one map row),
+// and reads its four 16-byte chunks at ((4 (gt & 1) + u) ^ ((gt >> 1) & 7)) — conflict-free ld.shared.v4 although
+// the lane stride is 64 bytes. (64-byte TMA rows with the 64-byte swizzle work too but stream 4 % slower.)
+// Owning a contiguous run makes the soft-arg-max bookkeeping per TILE instead of per 16-byte chunk: one
+// (column, row) position, one pair of first-moment FFMA2, one suffix-sum pass over the run.
 #ifndef MVGEO_DEC_MINB
 #define MVGEO_DEC_MINB 2  // measured: 2 CTAs/SM without a register cap beat 3 CTAs/SM at 64 registers (spills)
 #endif
+constexpr int kRunBytes = 64;   // bytes one thread owns per tile
+constexpr int kRowBytes = 128;  // TMA row = two runs
 // MSE: the same pass also accumulates sum (pred - g)^2 per map against the separable Gaussian target
 // g(x, y) = ex[x] * ey[y] built in shared memory per map (W + H exponentials, as csrc/encode.cu does) — the
 // training step's heat-map loss (nn.MSELoss, model/MvRoPose_FR3.py:846-847) and the decode of the same
 // prediction read the maps ONCE.
 template <int DT, int MODE, int U, int STAGES, int G, bool MSE = false>
-__global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_tma_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
+    decode_tma_kernel(const DecodeParams p, const __grid_constant__ TensorMaps tms) {
   static_assert(!MSE || MODE == MVGEO_SOFT_NONE, "the fused loss pass decodes the hard peak only");
+  static_assert(U * 16 == kRunBytes, "a run is four 16-byte chunks");
   using E = Elem<DT>;
   constexpr int PER = E::kPerChunk;
+  constexpr int EPR = U * PER;       // elements per run
   constexpr int NW = kDecWarps / G;  // consumer warps per group
   constexpr int NT = NW * 32;
   constexpr int kTile = NT * U;  // chunks per tile of one group
@@ -310,12 +339,12 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
   __shared__ BlockScratch sc[G];
   __shared__ __align__(8) uint64_t full_bar[G][STAGES];
   __shared__ __align__(8) uint64_t empty_bar[G][STAGES];
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];  // the 128-byte swizzle pattern repeats every 1024 bytes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = p.chunks_per_map;
-  const int n_full = n / kTile;                      // tiles without padding
-  const int n_tiles = (n + kTile - 1) / kTile;       // n_full or n_full + 1
+  const int rows = p.rows_per_map;                   // 64-byte runs per map
+  const int n_full = rows / NT;                      // tiles without padding
+  const int n_tiles = (rows + NT - 1) / NT;          // n_full or n_full + 1
   const int64_t step = (int64_t)gridDim.x * G;
 
   if (tid == 0) {
@@ -341,13 +370,24 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
     if (lane == 0) {
       int s = 0, k = 0;  // slot, and how many times the ring has wrapped
       for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
-        const char* seg = map_ptr(p, map);
+        // map (b, v, k) -> view v's tensor map and the map's first row inside that view
+        int v = 0;
+        int64_t local = map;
+        if (p.n_views > 1) {
+          const int64_t f = map / p.k_per_view;
+          const int64_t b = f / p.n_views;
+          v = (int)(f - b * p.n_views);
+          local = b * p.k_per_view + (map - f * p.k_per_view);
+        }
+        const CUtensorMap* tm = &tms.m[v];
+        const int row0 = (int)(local * (rows / 2));  // in 128-byte rows (maps are whole rows)
         for (int t = 0; t < n_tiles; ++t) {
           // before re-using a slot for the k-th time, wait for the consumers' (k-1)-th release of it
           if (k > 0) mbar_wait(empty_s + 8 * s, (uint32_t)((k - 1) & 1));
-          const uint32_t bytes = (uint32_t)min(kTile, n - t * kTile) * 16u;
-          mbar_arrive_expect_tx(full_s + 8 * s, bytes);
-          bulk_copy_g2s(ring_s + s * kTileBytes, seg + (size_t)t * kTileBytes, bytes, full_s + 8 * s);
+          // the box is always delivered whole: rows past the end of the tensor arrive as zeros, rows of the
+          // NEXT map as that map's data — the consumers mask both (they know how many runs the map has)
+          mbar_arrive_expect_tx(full_s + 8 * s, kTileBytes);
+          tma_load_rows(ring_s + s * kTileBytes, tm, row0 + t * (NT / 2), full_s + 8 * s);
           if (++s == STAGES) {
             s = 0;
             ++k;
@@ -359,56 +399,43 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
   }
 
   // --------------------------------- consumers ---------------------------------------------
-  const int gt = tid - g * NT;  // thread index inside the group
+  const int gt = tid - g * NT;  // thread index inside the group = the row of the tile this thread owns
   const int lw = gt >> 5;
   const int bar = 1 + g;
   BlockScratch& scr = sc[g];
-  const uint32_t my_s = ring_s + (uint32_t)gt * 16;  // this thread's first chunk of slot 0
-  // behind the rings: the raw chunks of every thread's best slice so far ([g][u][gt], 16 KB per CTA:
-  // the epilogue finds the first maximal element there, not in global memory), and every thread's
-  // tile-0 chunk positions ([g][2][gt] float4: computed once per CTA, the maps all have one shape)
+  const uint32_t my_s = ring_s + (uint32_t)(gt >> 1) * kRowBytes;  // this thread's 128-byte row in slot 0
+  // 128-byte swizzle: 16-byte chunk c of row r lives at c ^ (r & 7); this thread's chunk u is c = 4 (gt & 1) + u
+  const uint32_t sw = (uint32_t)((((gt & 1) << 2) ^ ((gt >> 1) & 7)) << 4);
+  // behind the rings: the raw chunks of every thread's best run so far ([g][u][gt], 16 KB per CTA: the
+  // epilogue finds the first maximal element there, not in global memory) ...
   const uint32_t cand_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + (uint32_t)(g * kTile + gt) * 16;
-  const uint32_t pos_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + (uint32_t)(g * 2 * NT + gt) * 16;
   // ... and every thread's per-map soft-arg-max totals (32 bytes each)
-  const uint32_t tot_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 32 +
-                         (uint32_t)(g * NT + gt) * 32;
+  const uint32_t tot_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + (uint32_t)(g * NT + gt) * 32;
 
   // Soft-arg-max geometry: coordinates are relative to the map centre; from one tile to the next a
-  // chunk advances by (step_y rows, step_x columns) with at most one row wrap.
+  // run advances by (step_y rows, step_x columns) with at most one row wrap.
   const float ox = 0.5f * (float)p.W, oy = 0.5f * (float)p.H, Wf = (float)p.W;
   const float x_hi = Wf - ox;  // first column value that belongs to the next row
-  const float step_y = (float)((kTile * PER) / p.W), step_x = (float)((kTile * PER) % p.W);
+  const int step_yi = (NT * EPR) / p.W, step_xi = (NT * EPR) % p.W;
+  const float step_y = (float)step_yi, step_x = (float)step_xi;
+  const int e00 = gt * EPR, y00 = e00 / p.W, x00 = e00 - y00 * p.W;  // this thread's run of tile 0
   const f32x2 beta2 = pack2(p.beta_log2e, p.beta_log2e);
   const float window = kEpochWindow / p.beta_log2e;
   const float kNegInf = __int_as_float(0xff800000);
 
   // MSE: behind the totals, one table of ex[0..Wp) and ey[0..H) per consumer group
   const int Wp = (p.W + 3) & ~3;
-  const uint32_t tab_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 64 +
+  const uint32_t tab_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 32 +
                          (uint32_t)g * (uint32_t)(Wp + ((p.H + 3) & ~3)) * 4;
-  const int mse_step_y = (kTile * PER) / p.W, mse_step_x = (kTile * PER) % p.W;
-  static_assert(U == 4, "positions are kept as two float4 per thread");
-  if (MODE == MVGEO_SOFT_GLOBAL) {  // position of chunk u of tile 0: private to the thread, no barrier needed
-    float px0[U], py0[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e0 = (u * NT + gt) * PER;
-      const int y0 = e0 / p.W;
-      px0[u] = (float)(e0 - y0 * p.W) - ox;
-      py0[u] = (float)y0 - oy;
-    }
-    sts128(pos_s, make_uint4(__float_as_uint(px0[0]), __float_as_uint(px0[1]), __float_as_uint(px0[2]), __float_as_uint(px0[3])));
-    sts128(pos_s + NT * 16, make_uint4(__float_as_uint(py0[0]), __float_as_uint(py0[1]), __float_as_uint(py0[2]), __float_as_uint(py0[3])));
-  }
 
   int s = 0;
   uint32_t ph = 0;
   for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
     float run_max = kNegInf;
-    int run_tile = gt < n ? 0 : -1;
+    int run_tile = gt < rows ? 0 : -1;
     SoftAcc a = {0.f, kNegInf, kNegInf, 0ull, 0ull, 0ull, 0ull};
     if (MODE == MVGEO_SOFT_GLOBAL) totals_store(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
-    int ix[U], iy[U];
+    int ix = x00, iy = y00;
     f32x2 mse_acc = 0ull;
     if (MSE) {
       // the map's separable Gaussian tables (consumers of this group only; the previous map's last table
@@ -419,45 +446,32 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
         const float d = i < p.W ? (float)i - cx : (float)(i - p.W) - cy;
         sts32f(tab_s + (uint32_t)(i < p.W ? i : Wp + i - p.W) * 4, okc ? ex2_approx(-d * d * p.mse_k) : 0.f);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int e0 = (u * NT + gt) * PER;
-        iy[u] = e0 / p.W;
-        ix[u] = e0 - iy[u] * p.W;
-      }
       group_sync<NW>(bar);
     }
-    float fx[U], fy[U];
-    if (MODE == MVGEO_SOFT_GLOBAL) {
-      const uint4 qx = lds128(pos_s), qy = lds128(pos_s + NT * 16);
-      fx[0] = __uint_as_float(qx.x); fx[1] = __uint_as_float(qx.y); fx[2] = __uint_as_float(qx.z); fx[3] = __uint_as_float(qx.w);
-      fy[0] = __uint_as_float(qy.x); fy[1] = __uint_as_float(qy.y); fy[2] = __uint_as_float(qy.z); fy[3] = __uint_as_float(qy.w);
-    }
+    float fx = (float)x00 - ox, fy = (float)y00 - oy;
 
-    // One tile: wait for the slot, take the thread's slice into registers, arg-max bookkeeping,
+    // One tile: wait for the slot, take the thread's run into registers, arg-max bookkeeping,
     // hand the slot back, then (global soft mode) the exponentials. FULL = no padding in the tile.
     auto tile_body = [&](auto full_tag, int t) {
       constexpr bool FULL = decltype(full_tag)::value;
       mbar_wait(full_s + 8 * s, ph);
       const uint32_t src = my_s + s * kTileBytes;
+      const bool live = FULL || (t * NT + gt < rows);  // rows past the map's end belong to the next map / nobody
       uint4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (FULL || t * kTile + u * NT + gt < n)
-          v[u] = lds128(src + u * NT * 16);
-        else
-          v[u] = E::neg_inf_chunk();
+        v[u] = lds128(src + (((uint32_t)u << 4) ^ sw));
+        if (!FULL && !live) v[u] = E::neg_inf_chunk();
       }
-      // vertical (packed) maximum over the thread's slice, then ONE horizontal step and ONE
-      // running-maximum update per tile. The slice maximum is canonicalised (+0.0f turns -0 into
+      // vertical (packed) maximum over the thread's run, then ONE horizontal step and ONE
+      // running-maximum update per tile. The run maximum is canonicalised (+0.0f turns -0 into
       // +0) so that the update test is a bit comparison of max.NaN results: equal values, -0/+0
-      // and NaN/NaN all keep the FIRST tile. Only the tile NUMBER is remembered (one predicated
-      // move); the epilogue re-reads the winning slice of the one thread that holds the maximum.
+      // and NaN/NaN all keep the FIRST tile.
       uint32_t vm = E::vmax(v[0]);
 #pragma unroll
       for (int u = 1; u < U; ++u) vm = E::vmerge(vm, E::vmax(v[u]));
       const float sm = E::vfinish(vm) + 0.0f;
-      // every register of the slice has been consumed by the maximum: hand the slot back to the
+      // every register of the run has been consumed by the maximum: hand the slot back to the
       // producer BEFORE the exponentials, so the refill overlaps the arithmetic
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_s + 8 * s);
@@ -466,21 +480,21 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
         ph ^= 1;
       }
       const float nm = max_nan_f32(run_max, sm);
-      if (__float_as_uint(nm) != __float_as_uint(run_max)) {  // strictly better: park the slice in shared memory
+      if (__float_as_uint(nm) != __float_as_uint(run_max)) {  // strictly better: park the run in shared memory
         run_tile = t;
 #pragma unroll
         for (int u = 0; u < U; ++u) sts128(cand_s + u * NT * 16, v[u]);
       }
       run_max = nm;
       if (MSE) {
+        if (live) {  // padding must not reach the loss
+          const float gy = -lds32f(tab_s + (uint32_t)(Wp + iy) * 4);
+          const f32x2 ngy = pack2(gy, gy);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (FULL || t * kTile + u * NT + gt < n) {  // padding must not reach the loss
-            const float gy = -lds32f(tab_s + (uint32_t)(Wp + iy[u]) * 4);
-            const f32x2 ngy = pack2(gy, gy);
+          for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int h = 0; h < PER / 4; ++h) {
-              const uint4 gx = lds128(tab_s + (uint32_t)(ix[u] + 4 * h) * 4);
+              const uint4 gx = lds128(tab_s + (uint32_t)(ix + u * PER + 4 * h) * 4);
               float lo, hi;
               E::pair(v[u], 2 * h, lo, hi);
               f32x2 d = fma2(pack2(__uint_as_float(gx.x), __uint_as_float(gx.y)), ngy, pack2(lo, hi));
@@ -489,19 +503,23 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
               d = fma2(pack2(__uint_as_float(gx.z), __uint_as_float(gx.w)), ngy, pack2(lo, hi));
               mse_acc = fma2(d, d, mse_acc);
             }
-          }
-          ix[u] += mse_step_x;
-          iy[u] += mse_step_y;
-          if (ix[u] >= p.W) {
-            ix[u] -= p.W;
-            ++iy[u];
-          }
+        }
+        ix += step_xi;
+        iy += step_yi;
+        if (ix >= p.W) {
+          ix -= p.W;
+          ++iy;
         }
       }
+      // (A data-dependent shortcut was measured and rejected: publishing the group's running maximum in shared
+      // memory and skipping tiles whose runs are all 32/beta below it lifts sharp-peak / large-beta maps to 6.9 TB/s
+      // but costs every other regime 7 %, and — because the skip depends on when another warp's atomicMax lands —
+      // it makes the last bits of kp_soft timing-dependent. Results here are bit-identical run to run and however
+      // the frames are sharded.)
       if (MODE == MVGEO_SOFT_GLOBAL) {
-        // rare: the slice leaves the epoch's window (first finite slice, climbing the peak, coming back down)
-        // An epoch that began by CLIMBING (a genuine peak) ends when the slices come back down; an epoch
-        // that began at the first finite slice or by coming down has no lower bound: plain noise whose slice
+        // rare: the run leaves the epoch's window (first finite run, climbing the peak, coming back down).
+        // An epoch that began by CLIMBING (a genuine peak) ends when the runs come back down; an epoch
+        // that began at the first finite run or by coming down has no lower bound: plain noise whose run
         // maxima wander by more than the window (uniform maps at large beta) would otherwise fold in most tiles.
         if (sm > a.ref_hi || (sm < a.ref_lo && sm > kNegInf)) {
           const bool climbed = sm > a.ref_hi && a.ref_hi > kNegInf;
@@ -511,35 +529,41 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
           a.ref_lo = climbed ? sm - window : kNegInf;
         }
         const f32x2 nb2 = pack2(a.nb, a.nb);
+        // The run's 2-element groups i = 0 .. NP-1 (element 2i, 2i+1), processed as two halves so that the
+        // dependent add chains stay short. Suffix sums t_i = w_i + ... + w_last of a half give its sum cs = t_0
+        // and sum_i i*w_i = t_1 + t_2 + ...: adds only, no per-element constants. For the run:
+        //   sum_j j*w_j = 2 * sum_i i*(w_i.lo + w_i.hi) + sum_i w_i.hi      (the last term is the odd half of a.s,
+        //   added at the fold), and the upper half's groups carry an extra offset NP/2.
+        constexpr int NP = EPR / 2, HP = NP / 2, PPC = PER / 2;  // groups per run / per half / per chunk
+        f32x2 cs[2], sj[2];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          // w[i] = weights of elements (2i, 2i+1). Suffix sums t_i = w_i + ... + w_last give the chunk
-          // sum cs = t_0 and sum_i i*w_i = t_1 + t_2 + ...: adds only, no per-element constants.
-          // (sum_j j*w_j over the chunk = 2 * sum_i i*(w_i.lo + w_i.hi) + sum_i w_i.hi; the last
-          // term is the odd half of a.s and is added in the epilogue.)
-          f32x2 w[PER / 2];
+        for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-          for (int i = 0; i < PER / 2; ++i) {
+          for (int i = HP - 1; i >= 0; --i) {
+            const int gi = hf * HP + i;  // group index in the run
             float lo, hi;
-            E::pair(v[u], i, lo, hi);
+            E::pair(v[gi / PPC], gi % PPC, lo, hi);
             unpack2(fma2(pack2(lo, hi), beta2, nb2), lo, hi);
-            w[i] = pack2(ex2_approx(lo), ex2_approx(hi));  // -inf padding: weight 0
+            const f32x2 w = pack2(ex2_approx(lo), ex2_approx(hi));  // -inf padding: weight 0
+            if (i == HP - 1) {
+              cs[hf] = w;
+            } else {
+              sj[hf] = (i == HP - 2) ? cs[hf] : add2(sj[hf], cs[hf]);
+              cs[hf] = add2(cs[hf], w);
+            }
           }
-          f32x2 cs = w[PER / 2 - 1];
-#pragma unroll
-          for (int i = PER / 2 - 2; i >= 0; --i) {
-            a.sj = add2(a.sj, cs);
-            cs = add2(cs, w[i]);
-          }
-          a.s = add2(a.s, cs);
-          a.sx = fma2(cs, pack2(fx[u], fx[u]), a.sx);
-          a.sy = fma2(cs, pack2(fy[u], fy[u]), a.sy);
-          fx[u] += step_x;
-          fy[u] += step_y;
-          if (fx[u] >= x_hi) {
-            fx[u] -= Wf;
-            fy[u] += 1.0f;
-          }
+        }
+        const f32x2 ct = add2(cs[0], cs[1]);
+        a.s = add2(a.s, ct);
+        a.sj = add2(a.sj, add2(sj[0], sj[1]));
+        a.sj = fma2(cs[1], pack2((float)HP, (float)HP), a.sj);
+        a.sx = fma2(ct, pack2(fx, fx), a.sx);
+        a.sy = fma2(ct, pack2(fy, fy), a.sy);
+        fx += step_x;
+        fy += step_y;
+        if (fx >= x_hi) {
+          fx -= Wf;
+          fy += 1.0f;
         }
       }
     };
@@ -555,22 +579,21 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB) decode_t
 #pragma unroll
     for (int w = 1; w < NW; ++w) mk = max(mk, scr.key[w]);
     const float M = ord_val(mk);
-    // 2. the first maximal element: only threads that hold the maximum look at their winning slice
+
+    // 2. the first maximal element: only threads that hold the maximum look at their winning run
     //    (parked in shared memory by the streaming loop), lowest index wins
     int my_idx = 0x7fffffff;
     const bool isn = (M != M);
     // (an all -inf map parked nothing: every element is maximal and index 0 wins, see below)
     if (run_tile >= 0 && M != kNegInf && (isn ? (run_max != run_max) : (__float_as_uint(run_max) == __float_as_uint(M)))) {
+      const int e0 = (run_tile * NT + gt) * EPR;
 #pragma unroll
       for (int u = U - 1; u >= 0; --u) {  // descending: the lowest index sticks
-        const int c = (run_tile * U + u) * NT + gt;
-        if (c < n) {
-          const uint4 ch = lds128(cand_s + u * NT * 16);
+        const uint4 ch = lds128(cand_s + u * NT * 16);
 #pragma unroll
-          for (int j = PER - 1; j >= 0; --j) {
-            const float e = E::get(ch, j);
-            if (isn ? (e != e) : (e == M)) my_idx = c * PER + j;
-          }
+        for (int j = PER - 1; j >= 0; --j) {
+          const float e = E::get(ch, j);
+          if (isn ? (e != e) : (e == M)) my_idx = e0 + u * PER + j;
         }
       }
     }
@@ -702,10 +725,48 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 #endif
 constexpr int kTmaU = MVGEO_TMA_U;
 constexpr int kTmaStages = MVGEO_TMA_STAGES;
-// per CTA: the rings, one tile of parked candidate slices, two float4 of chunk positions and the 32-byte
-// soft-arg-max totals per thread
-constexpr size_t kRingBytes = (size_t)(kTmaStages + 1) * kTmaU * kDecThreads * 16 + (size_t)kDecThreads * 64;
+// per CTA: the rings, one tile of parked candidate runs and the 32-byte soft-arg-max totals per thread
+constexpr size_t kRingBytes = (size_t)(kTmaStages + 1) * kTmaU * kDecThreads * 16 + (size_t)kDecThreads * 32;
 constexpr int kMaxDevices = 64;
+
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static std::atomic<void*> cached{nullptr};  // a pure function of the driver: racing threads store the same pointer
+  void* f = cached.load(std::memory_order_acquire);
+  if (!f) {
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !f)
+      return nullptr;
+    cached.store(f, std::memory_order_release);
+  }
+  return reinterpret_cast<EncodeTiledFn>(f);
+}
+
+// One tensor map per base pointer: [rows of 128 bytes] x [128 bytes], box = box_rows x 128 bytes, 128-byte swizzle.
+static int build_tensor_maps(const DecodeParams& p, int box_rows, TensorMaps& tms) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return MVGEO_EUNSUPPORTED;
+  memset(&tms, 0, sizeof(tms));
+  const int64_t maps_per_view = p.n_views == 1 ? p.n_maps : p.n_maps / p.n_views;
+  const uint64_t rows_total = (uint64_t)maps_per_view * (uint64_t)(p.rows_per_map / 2);
+  if (rows_total > 0x7fffffffull) return MVGEO_EUNSUPPORTED;  // TMA coordinates are 32-bit signed (137 GB per view)
+  for (int v = 0; v < p.n_views; ++v) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)rows_total};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kRowBytes};
+    const cuuint32_t box[2] = {(cuuint32_t)kRowBytes, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tms.m[v], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(p.view_base[v]), gdim, gstride, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MVGEO_EINVAL;
+  }
+  return MVGEO_OK;
+}
 
 constexpr size_t kMseTableMax = 16 * 1024;  // shared memory of the fused loss pass's Gaussian tables (2 CTAs/SM still fit)
 
@@ -720,6 +781,9 @@ static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
   const size_t smem = kSmemMax;  // constant per instantiation: the cached occupancy is exact
   if (MSE && (size_t)G * (((p.W + 3) & ~3) + ((p.H + 3) & ~3)) * 4 > kMseTableMax)
     return MVGEO_EUNSUPPORTED;  // very wide / tall maps: use the two separate passes
+  TensorMaps tms;
+  const int rc = build_tensor_maps(p, kDecThreads / G / 2, tms);
+  if (rc) return rc;
   static std::atomic<int> cache[kMaxDevices];
   int dev = 0;
   MVGEO_CUDA(cudaGetDevice(&dev));
@@ -735,7 +799,7 @@ static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
   }
   const int64_t wanted = (p.n_maps + G - 1) / G;
   const unsigned grid = (unsigned)(wanted < resident_ctas ? wanted : resident_ctas);
-  kern<<<grid, kDecThreads + 32 * G, smem, st>>>(p);
+  kern<<<grid, kDecThreads + 32 * G, smem, st>>>(p, tms);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }
@@ -784,8 +848,9 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.map_bytes = (int64_t)H * W * esize;
   // Work decomposition is a function of the map shape only (never of n_maps or the data), so results
   // are bit-identical however the frames are sharded across GPUs.
-  bool vec = (p.map_bytes % 16 == 0);
-  if (soft_mode == MVGEO_SOFT_GLOBAL && (W * esize) % 16 != 0) vec = false;  // a chunk must not straddle rows
+  // streaming kernel: maps made of whole 64-byte runs; global soft mode: runs that never straddle two rows
+  bool vec = (p.map_bytes % kRowBytes == 0);
+  if (soft_mode == MVGEO_SOFT_GLOBAL && (W * esize) % kRunBytes != 0) vec = false;
   for (int v = 0; v < n_views; ++v) {
     if (!view_maps[v]) return MVGEO_ENULL;
     p.view_base[v] = view_maps[v];
@@ -810,7 +875,7 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.score = score;
   p.kp_hard = kp_hard;
   p.kp_soft = kp_soft;
-  p.chunks_per_map = vec ? (int)(p.map_bytes / 16) : 0;
+  p.rows_per_map = vec ? (int)(p.map_bytes / kRunBytes) : 0;
   // small maps -> several consumer groups per CTA, one map stream each (epilogues overlap):
   // 4 up to 112 KB (native 128x128 fp32, C1), 2 up to 160 KB (C2 / C3), measured; larger: one group.
   const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
@@ -858,8 +923,10 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   if (n_maps == 0) return MVGEO_OK;
   if (!maps || !kp_target || !partial || !loss) return MVGEO_ENULL;
   const int esize = dtype == MVGEO_F32 ? 4 : 2;
-  // the fused pass is the streaming kernel only: 16-byte aligned maps whose rows hold whole 16-byte chunks
-  if ((reinterpret_cast<uintptr_t>(maps) & 15) || (W * esize) % 16 != 0) return MVGEO_EUNSUPPORTED;
+  // the fused pass is the streaming kernel only: 16-byte aligned maps of whole 128-byte TMA rows whose image rows
+  // hold whole 64-byte runs
+  if ((reinterpret_cast<uintptr_t>(maps) & 15) || (W * esize) % kRunBytes != 0 || ((int64_t)H * W * esize) % kRowBytes != 0)
+    return MVGEO_EUNSUPPORTED;
   DecodeParams p = {};
   p.view_base[0] = maps;
   p.n_views = 1;
@@ -868,7 +935,7 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   p.map_bytes = (int64_t)H * W * esize;
   p.H = H;
   p.W = W;
-  p.chunks_per_map = (int)(p.map_bytes / 16);
+  p.rows_per_map = (int)(p.map_bytes / kRunBytes);
   p.scale_x = scale_x;
   p.scale_y = scale_y;
   p.apply_sigmoid = apply_sigmoid;

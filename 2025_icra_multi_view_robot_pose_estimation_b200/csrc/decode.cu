@@ -7,29 +7,32 @@
 // Roofline: HBM. Every map byte is read from DRAM exactly once in EVERY mode and for EVERY data
 // distribution (algorithmic bytes per map = H*W*sizeof(dtype); outputs are 28 B per map). Design:
 //   * PERSISTENT kernel: (SMs x resident CTAs) CTAs, each walking maps blockIdx.x, +gridDim.x, ...
-//     One elected producer lane per map stream issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of 8 KB
-//     tiles into a 4-stage shared-memory ring with full/empty mbarriers; 8 consumer warps read
-//     the tiles with ld.shared.v4. Bytes in flight are set by the ring, not by registers, and the
-//     producer keeps prefetching the NEXT map while the consumers are in the latency-bound per-map
-//     epilogue (consumer-only named barrier), so the DRAM pipe never drains;
+//     One elected producer lane per map stream issues 2-D tensor-map TMA loads (cp.async.bulk.tensor.2d,
+//     SASS UTMALDG.2D; the maps are described as a tensor of 128-byte rows) of 16 KB / G tiles into a
+//     4-stage shared-memory ring with full/empty mbarriers, written with the 128-byte hardware swizzle so
+//     that every consumer thread owns a RUN of 64 contiguous map bytes and still reads it with
+//     conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by registers, and the
+//     producer keeps prefetching the NEXT map while the consumers are in the per-map epilogue
+//     (consumer-only named barrier), so the DRAM pipe never drains;
 //   * arg-max: a packed max.NaN tree per 16-byte chunk (bf16x2 / f16x2 SIMD for 16-bit maps) and ONE
-//     running-maximum update per thread per tile (a "slice" = the U chunks a thread owns in a
-//     tile); the raw chunks of the best slice stay in registers, so the first maximal element is
-//     resolved without touching memory again; then a warp-shuffle / shared-memory (value, index)
-//     reduction with torch.argmax's first-maximum, NaN-is-maximal ordering;
+//     running-maximum update per thread per tile; the raw chunks of the best run are parked in shared
+//     memory, so the first maximal element is resolved without touching global memory again; group
+//     maximum and lowest index are one redux.sync each, with torch.argmax's first-maximum,
+//     NaN-is-maximal ordering;
 //   * global soft-arg-max: ONLINE softmax in the same streaming loop. Every thread keeps
-//     (sum w, sum w x, sum w y) relative to its own running maximum m_t, w = 2^(h*beta' - m_t*beta'),
-//     one FFMA + one MUFU.EX2 + two accumulation ops per element (x moments are formed per 16-byte
-//     chunk: sum w and sum j*w, the chunk's column / row applied once per chunk), and rescales its
-//     three sums when m_t grows (a few times per map). The epilogue rescales every thread to the
-//     true maximum M with ONE exp per thread. Cost and DRAM traffic are independent of the data
-//     (round 1 re-read every slice within 32/beta of the maximum: free for a sharp peak at large
-//     beta, but up to 2x traffic plus a scattered gather for flat / low-amplitude maps or small beta);
+//     (sum w, sum w x, sum w y) with w = 2^(h*beta' - ref*beta'): one FFMA2 per two elements, one MUFU.EX2
+//     per element, moments from suffix sums of the run (FADD2 only), position applied once per tile. The
+//     reference moves only when a run leaves a +-16 log2 window ("epochs", folded in double), so there is
+//     no per-tile rescale and the f32 sums never mix magnitudes. Cost and DRAM traffic are independent of
+//     the data (round 1 re-read every slice within 32/beta of the maximum: free for a sharp peak at large
+//     beta, but 1.06 TB/s for flat / low-amplitude maps or small beta);
 //   * maps up to 112 KB run 4 independent map streams per CTA (consumer groups of 2 warps, each
 //     with its own ring, mbarriers, named barrier and producer warp) so that epilogues overlap;
 //   * V per-view base pointers (the reference's dict view -> (B,K,H,W), model/MvRoPose_FR3.py:625)
-//     are walked by ONE launch: map m = (b, v, k) is read from view v's tensor, results land in
-//     [B,V,K] order. No stack copy, no per-view launch.
+//     are walked by ONE launch through V tensor maps: map m = (b, v, k) is read from view v's tensor,
+//     results land in [B,V,K] order. No stack copy, no per-view launch;
+//   * MSE variant: the heat-map loss against on-the-fly Gaussian targets from the same registers
+//     (one-read training step).
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <atomic>

@@ -1240,3 +1240,106 @@ def test_decode_and_mse_one_read(mv, dtype, HW):
     assert torch.equal(tq.grad, t2.grad)
     l2 = mv.heatmap_mse_loss(t, kp, 5.0, 1e4)
     assert abs(float(loss) - float(l2)) <= 2e-6 * abs(float(l2))
+
+
+def test_round2_kernels_write_only_their_outputs(mv):
+    """Canaries around every output of the round-2 entry points (mvgeo_decode_views, mvgeo_decode_mse, mvgeo_pnp_solve),
+    NaN guards around their map inputs: the 2-D TMA tiles of the last map of a tensor reach past its end by design
+    (zero-filled / next rows) and must be masked."""
+    import ctypes as C
+    lib = mv._lib.load()
+    rng = np.random.default_rng(5)
+    st = torch.cuda.current_stream().cuda_stream
+    CAN = 96
+
+    def guarded(n, dt=torch.float32):
+        t = torch.full((CAN + n + CAN,), -777, dtype=dt, device=DEV)
+        return t, t.data_ptr() + CAN * t.element_size()
+
+    def intact(t, n):
+        return bool((t[:CAN] == -777).all() and (t[CAN + n:] == -777).all() and not (t[CAN:CAN + n] == -777).all())
+
+    Bn, V, K, H, W = 5, 3, 7, 40, 64
+    guard = 1 << 14
+    views, seen = [], []
+    for v in range(V):
+        buf = torch.full((guard + Bn * K * H * W + guard,), float("nan"), dtype=torch.bfloat16, device=DEV)
+        m = buf[guard:guard + Bn * K * H * W].view(Bn, K, H, W)
+        m.copy_(torch.from_numpy(rng.normal(size=(Bn, K, H, W)).astype(np.float32)).to(DEV))
+        views.append(m)
+        seen.append(m.float().cpu().numpy())
+    seen = np.stack(seen, axis=1)                                  # (B,V,K,H,W)
+    n = Bn * V * K
+    o = {k: guarded(n * wdt, dt) for k, wdt, dt in (("idx", 1, torch.int32), ("peak", 1, torch.float32), ("score", 1, torch.float32),
+                                                    ("kp_hard", 2, torch.float32), ("kp_soft", 2, torch.float32))}
+    ptrs = (C.c_void_p * V)(*[v.data_ptr() for v in views])
+    assert lib.mvgeo_decode_views(ptrs, V, 1, Bn, K, H, W, 1.0, 1.0, 1, 20.0, 0, 0, o["idx"][1], o["peak"][1], o["score"][1],
+                                  o["kp_hard"][1], o["kp_soft"][1], st) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o["idx"][0][CAN:CAN + n].cpu().numpy().reshape(Bn, V, K), O.argmax_first(seen)[0])
+    ks = o["kp_soft"][0][CAN:CAN + 2 * n].cpu().numpy().reshape(Bn, V, K, 2)
+    assert np.abs(ks - O.soft_argmax(seen, 20.0, "global")).max() < 1e-3
+    for k, wdt in (("idx", 1), ("peak", 1), ("score", 1), ("kp_hard", 2), ("kp_soft", 2)):
+        assert intact(o[k][0], n * wdt), k
+    # fused loss pass
+    m0 = views[0]
+    nm = Bn * K
+    tgt = torch.from_numpy(np.stack([rng.uniform(0, W, nm), rng.uniform(0, H, nm)], 1).astype(np.float32)).to(DEV)
+    idx, pidx = guarded(nm, torch.int32)
+    pk, ppk = guarded(nm)
+    sc, psc = guarded(nm)
+    kh, pkh = guarded(2 * nm)
+    part, ppart = guarded(nm)
+    ls, pls = guarded(1)
+    assert lib.mvgeo_decode_mse(m0.data_ptr(), 1, nm, H, W, 1.0, 1.0, 0, tgt.data_ptr(), 3.0, 5.0, pidx, ppk, psc, pkh, ppart, pls, st) == 0
+    torch.cuda.synchronize()
+    for t, cnt in ((idx, nm), (pk, nm), (sc, nm), (kh, 2 * nm), (part, nm), (ls, 1)):
+        assert intact(t, cnt)
+    ref_loss, _ = O.heatmap_mse(seen[:, 0].reshape(nm, H, W), tgt.cpu().numpy(), 3.0, 5.0)
+    assert abs(float(ls[CAN]) - ref_loss) <= 1e-5 * abs(ref_loss)
+    np.testing.assert_array_equal(idx[CAN:CAN + nm].cpu().numpy(), O.argmax_first(seen[:, 0].reshape(nm, H, W))[0])
+    # PnP without a prior
+    chain = mv.Chain.builtin("fr5")
+    Kp = chain.n_points
+    rig = mv.CameraRig.synthetic_ring_for("fr5", 2, distortion=True)
+    cams = mv.ops.cameras_to_device(rig, DEV)
+    q = torch.from_numpy(rng.uniform(-100, 100, (9, chain.n_joints)).astype(np.float32)).to(DEV)
+    X = mv.forward_kinematics(chain, q)[:, 0].contiguous()
+    kp = mv.project_points(X, rig)
+    rv, prv = guarded(9 * 2 * 3)
+    tv, ptv = guarded(9 * 2 * 3)
+    rm, prm = guarded(9 * 2)
+    sts, psts = guarded(9 * 2, torch.int32)
+    inl, pinl = guarded(9 * 2, torch.int32)
+    assert lib.mvgeo_pnp_solve(X.data_ptr(), 0, kp.data_ptr(), None, cams.data_ptr(), 9, 2, Kp, 0.0, 8.0, 20, prv, ptv, prm, psts, pinl, st) == 0
+    torch.cuda.synchronize()
+    for t, cnt in ((rv, 54), (tv, 54), (rm, 18), (sts, 18), (inl, 18)):
+        assert intact(t, cnt)
+    assert ((sts[CAN:CAN + 18] & 1) == 1).all()
+    np.testing.assert_allclose(tv[CAN:CAN + 54].cpu().numpy().reshape(9, 2, 3), np.broadcast_to(rig.t.astype(np.float32), (9, 2, 3)), atol=2e-3)
+
+
+def test_robot_pose_loss_differentiable_fk_term(mv):
+    """compat.robot_pose_loss: same value as the reference form with a detached proj_2d, and — extension — a FK term
+    that is differentiable in the angles when proj_2d is absent and a chain + camera are given."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(6)
+    chain = mv.Chain.from_dh([0.1, 0.3, 0.25, 0.0, 0.0, 0.08], [0.3, 0.0, 0.0, 0.3, 0.0, 0.1], [1.57, 0.0, 1.57, -1.57, 1.57, 0.0],
+                             [0.0] * 6, convention="standard", angle_scale=1.0, emit_base=False)
+    rig = mv.CameraRig.synthetic_ring(1)
+    ang = torch.from_numpy(rng.uniform(-1, 1, (5, 6)).astype(np.float32)).to(DEV).requires_grad_(True)
+    gt_kp = torch.from_numpy(rng.uniform(200, 900, (5, 6, 2)).astype(np.float32)).to(DEV)
+    gt_ang = torch.zeros((5, 6), device=DEV)
+    proj = mv.project_points(mv.forward_kinematics(chain, ang.detach())[:, 0], rig)[:, 0]          # (B,J,2), detached
+    pred = {"keypoints_2d": gt_kp + 1.0, "angles": ang, "proj_2d": proj}
+    ref = F.mse_loss(pred["keypoints_2d"], gt_kp) + F.mse_loss(ang, gt_ang) + 0.5 * F.mse_loss(proj, gt_kp)
+    a = mv.compat.robot_pose_loss(pred, gt_kp, gt_ang, 1.0, 1.0, 0.5)
+    assert abs(float(a) - float(ref)) <= 1e-6 * abs(float(ref))
+    pred2 = {"keypoints_2d": gt_kp + 1.0, "angles": ang}
+    b = mv.compat.robot_pose_loss(pred2, gt_kp, gt_ang, 1.0, 1.0, 0.5, chain=chain, cams=rig)
+    assert abs(float(b) - float(ref)) <= 1e-4 * abs(float(ref))
+    b.backward()
+    g_fk = ang.grad.clone()
+    ang.grad = None
+    F.mse_loss(ang, gt_ang).backward()
+    assert (g_fk - ang.grad).abs().max() > 0            # the FK term contributes a gradient the reference form cannot

@@ -26,7 +26,7 @@
 //     no per-tile rescale and the f32 sums never mix magnitudes. Cost and DRAM traffic are independent of
 //     the data (round 1 re-read every slice within 32/beta of the maximum: free for a sharp peak at large
 //     beta, but 1.06 TB/s for flat / low-amplitude maps or small beta);
-//   * maps up to 112 KB run 4 independent map streams per CTA (consumer groups of 2 warps, each
+//   * maps up to 2 MB run 4 independent map streams per CTA (consumer groups of 2 warps, each
 //     with its own ring, mbarriers, named barrier and producer warp) so that epilogues overlap;
 //   * V per-view base pointers (the reference's dict view -> (B,K,H,W), model/MvRoPose_FR3.py:625)
 //     are walked by ONE launch through V tensor maps: map m = (b, v, k) is read from view v's tensor,
@@ -215,18 +215,20 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 //
 // Epochs. The reference `ref` is NOT the running maximum (with a per-thread running maximum SOME lane
 // of a warp breaks its record in ~90% of the tiles and the whole warp pays a rescale: 15% of all issued
-// instructions). Floating point keeps its relative precision for weights far from 1, so an epoch lasts as
-// long as the slice maxima stay within kEpochWindow (log2 units) of ref. When a slice leaves the window
-// (the thread climbs the peak, or comes back down to the background after a climb) the epoch's sums are
-// folded, in DOUBLE, into the thread's per-map totals in shared memory and a new epoch starts at the new level.
-// This bounds the dynamic range inside the f32 accumulators: without it, once a thread has met the peak
-// every later background tile is rounded at the scale of the peak's first moment (lever arm to the map
-// centre: hundreds of pixels) — measured up to 3e-4 px when the background holds ~1e-3 of the weight.
-// Cost: nothing per element; the fold runs a handful of times per map in the threads that cross the peak.
-constexpr float kEpochWindow = 16.0f;
+// instructions). Floating point keeps its relative precision for weights far from 1, so the reference only
+// moves when a run maximum climbs more than kEpochWindow (log2 units) above it: the first finite run, and
+// the few runs in which a thread climbs the peak. At that moment — and every kFoldPeriod tiles regardless —
+// the epoch's f32 sums are folded, in DOUBLE, into the thread's per-map totals in shared memory and start
+// again from zero. The periodic fold bounds what f32 accumulation can lose: once a thread has met the peak
+// its first moments carry the lever arm to the map centre (hundreds of pixels) times the peak's mass, and
+// every later background tile added on top would be rounded at THAT scale — measured up to 3e-4 px when the
+// background holds ~1e-3 of the weight; with at most kFoldPeriod tiles per fold the bound is ~5e-5 px.
+// Cost: nothing per element; ~70 instructions per fold, i.e. ~2% of the loop.
+constexpr float kEpochWindow = 64.0f;  // range only: weights stay below 2^64, sums below 2^100
+constexpr int kFoldPeriod = 16;  // tiles (power of two)
 struct SoftAcc {
-  float nb;              // -ref * beta_log2e as rounded (the fold corrects with the SAME value)
-  float ref_hi, ref_lo;  // ref +- kEpochWindow / beta_log2e
+  float nb;      // -ref * beta_log2e as rounded (the fold corrects with the SAME value)
+  float ref_hi;  // ref + kEpochWindow / beta_log2e
   f32x2 s, sx, sy;       // sum w, sum w (x0 - ox), sum w (y - oy), x0 = the chunk's first column
   f32x2 sj;              // sum w i, i = index of the element's 2-element group inside its chunk
 };
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
   for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
     float run_max = kNegInf;
     int run_tile = gt < rows ? 0 : -1;
-    SoftAcc a = {0.f, kNegInf, kNegInf, 0ull, 0ull, 0ull, 0ull};
+    SoftAcc a = {0.f, kNegInf, 0ull, 0ull, 0ull, 0ull};
     if (MODE == MVGEO_SOFT_GLOBAL) totals_store(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
     int ix = x00, iy = y00;
     f32x2 mse_acc = 0ull;
@@ -520,16 +522,17 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
       // it makes the last bits of kp_soft timing-dependent. Results here are bit-identical run to run and however
       // the frames are sharded.)
       if (MODE == MVGEO_SOFT_GLOBAL) {
-        // rare: the run leaves the epoch's window (first finite run, climbing the peak, coming back down).
-        // An epoch that began by CLIMBING (a genuine peak) ends when the runs come back down; an epoch
-        // that began at the first finite run or by coming down has no lower bound: plain noise whose run
-        // maxima wander by more than the window (uniform maps at large beta) would otherwise fold in most tiles.
-        if (sm > a.ref_hi || (sm < a.ref_lo && sm > kNegInf)) {
-          const bool climbed = sm > a.ref_hi && a.ref_hi > kNegInf;
+        // Fold the epoch (rare, warp-uniform or nearly so): when a run climbs out of the window — first finite
+        // run, climbing the peak — the reference moves; and every kFoldPeriod tiles unconditionally, so that an
+        // accumulator that holds the peak's mass never takes more than kFoldPeriod background tiles on top
+        // (bounds the f32 rounding of the long tail after a peak, wherever in the map the peak sits).
+        const bool climb = sm > a.ref_hi;
+        if (climb || (t & (kFoldPeriod - 1)) == kFoldPeriod - 1) {
           epoch_fold(a, tot_s);
-          a.nb = -sm * p.beta_log2e;
-          a.ref_hi = sm + window;
-          a.ref_lo = climbed ? sm - window : kNegInf;
+          if (climb) {
+            a.nb = -sm * p.beta_log2e;
+            a.ref_hi = sm + window;
+          }
         }
         const f32x2 nb2 = pack2(a.nb, a.nb);
         // The run's 2-element groups i = 0 .. NP-1 (element 2i, 2i+1), processed as two halves so that the
@@ -721,10 +724,10 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 #define MVGEO_TMA_STAGES 4
 #endif
 #ifndef MVGEO_G4_MAX
-#define MVGEO_G4_MAX (112 * 1024)
+#define MVGEO_G4_MAX (2 * 1024 * 1024)
 #endif
 #ifndef MVGEO_G2_MAX
-#define MVGEO_G2_MAX (160 * 1024)
+#define MVGEO_G2_MAX (8 * 1024 * 1024)
 #endif
 constexpr int kTmaU = MVGEO_TMA_U;
 constexpr int kTmaStages = MVGEO_TMA_STAGES;
@@ -879,8 +882,9 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.kp_hard = kp_hard;
   p.kp_soft = kp_soft;
   p.rows_per_map = vec ? (int)(p.map_bytes / kRunBytes) : 0;
-  // small maps -> several consumer groups per CTA, one map stream each (epilogues overlap):
-  // 4 up to 112 KB (native 128x128 fp32, C1), 2 up to 160 KB (C2 / C3), measured; larger: one group.
+  // several consumer groups per CTA, one map stream each (one group's per-map epilogue overlaps the others'
+  // streaming): 4 groups up to 2 MB maps (every BASELINE config; measured +3 % at C2 and +5 % at C5 over 2 / 1
+  // groups), 2 up to 8 MB, one group (all 8 consumer warps on one map) beyond — a function of the map size only.
   const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
@@ -951,7 +955,9 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   p.mse_kp = kp_target;
   p.mse_k = kLog2e / (2.0f * sigma * sigma);
   p.mse_partial = partial;
-  const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
+  int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
+  // every consumer group holds its own pair of Gaussian tables: fewer groups for wide / tall maps (shape only)
+  while (groups > 1 && (size_t)groups * (((W + 3) & ~3) + ((H + 3) & ~3)) * 4 > kMseTableMax) groups >>= 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
   switch (dtype) {

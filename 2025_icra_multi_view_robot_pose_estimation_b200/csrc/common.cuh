@@ -185,6 +185,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// 2^t for two elements on the FMA / ALU pipes (no MUFU): t is clamped to >= -126 (the result is then 2^-126, not 0),
+// split by the magic-number add into n = round(t) and f = t - n in [-0.5, 0.5], 2^f by a degree-5 minimax polynomial
+// (relative error 2.2e-7 evaluated in f32, the same as ex2.approx), and n added to the exponent field. t <= 127.
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 t) {
+  float lo, hi;
+  unpack2(t, lo, hi);
+  t = pack2(fmaxf(lo, -126.0f), fmaxf(hi, -126.0f));
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f);  // 1.5 * 2^23
+  const f32x2 r = add2(t, magic);
+  const f32x2 f = sub2(t, sub2(r, magic));
+  f32x2 q = pack2(1.327637467e-03f, 1.327637467e-03f);
+  q = fma2(q, f, pack2(9.675514884e-03f, 9.675514884e-03f));
+  q = fma2(q, f, pack2(5.550713465e-02f, 5.550713465e-02f));
+  q = fma2(q, f, pack2(2.402212024e-01f, 2.402212024e-01f));
+  q = fma2(q, f, pack2(6.931469440e-01f, 6.931469440e-01f));
+  q = fma2(q, f, pack2(1.000000119e+00f, 1.000000119e+00f));
+  float rl, rh;
+  unpack2(r, rl, rh);
+  unpack2(q, lo, hi);
+  // the low mantissa bits of r hold n (two's complement); << 23 moves them onto the exponent field
+  lo = __uint_as_float(__float_as_uint(lo) + (__float_as_uint(rl) << 23));
+  hi = __uint_as_float(__float_as_uint(hi) + (__float_as_uint(rh) << 23));
+  return pack2(lo, hi);
+}
+
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);

@@ -16,18 +16,22 @@
 //     (consumer-only named barrier), so the DRAM pipe never drains;
 //   * arg-max: a packed max.NaN tree per 16-byte chunk (bf16x2 / f16x2 SIMD for 16-bit maps) and ONE
 //     running-maximum update per thread per tile; the raw chunks of the best run are parked in shared
-//     memory, so the first maximal element is resolved without touching global memory again; group
-//     maximum and lowest index are one redux.sync each, with torch.argmax's first-maximum,
-//     NaN-is-maximal ordering;
+//     memory, so the first maximal element is resolved without touching global memory again: warp
+//     maximum = one redux.sync, first run holding it = one redux.sync, first maximal element of that run =
+//     one ballot (lane j looks at element j), with torch.argmax's first-maximum, NaN-is-maximal ordering;
 //   * global soft-arg-max: ONLINE softmax in the same streaming loop. Every thread keeps
 //     (sum w, sum w x, sum w y) with w = 2^(h*beta' - ref*beta'): one FFMA2 per two elements, one MUFU.EX2
 //     per element, moments from suffix sums of the run (FADD2 only), position applied once per tile. The
-//     reference moves only when a run leaves a +-16 log2 window ("epochs", folded in double), so there is
-//     no per-tile rescale and the f32 sums never mix magnitudes. Cost and DRAM traffic are independent of
+//     reference moves only when a run climbs 64 log2 units above it, and the f32 sums are folded in double
+//     into per-thread totals at that moment and every 16 tiles ("epochs"): no per-tile rescale, and the f32
+//     rounding of a long background tail after a peak stays bounded. Cost and DRAM traffic are independent of
 //     the data (round 1 re-read every slice within 32/beta of the maximum: free for a sharp peak at large
 //     beta, but 1.06 TB/s for flat / low-amplitude maps or small beta);
 //   * maps up to 2 MB run 4 independent map streams per CTA (consumer groups of 2 warps, each
-//     with its own ring, mbarriers, named barrier and producer warp) so that epilogues overlap;
+//     with its own ring, mbarriers, named barrier and producer warp) so that epilogues overlap; maps up to
+//     32 KB (the reference-native 128x128 under bf16 autocast) run 8 ONE-WARP streams that feed themselves:
+//     lane 0 re-issues the TMA copy into the slot its own warp has just emptied — no producer warps, no
+//     empty barriers, every per-map reduction warp-wide (16 tiles per thread and map instead of 8: +13 %);
 //   * V per-view base pointers (the reference's dict view -> (B,K,H,W), model/MvRoPose_FR3.py:625)
 //     are walked by ONE launch through V tensor maps: map m = (b, v, k) is read from view v's tensor,
 //     results land in [B,V,K] order. No stack copy, no per-view launch;
@@ -96,6 +100,10 @@ struct BlockScratch {
 // reduce independently of one another and of the producer warps.
 template <int NW>
 __device__ __forceinline__ void group_sync(int bar) {
+  if (NW == 1) {  // a one-warp group
+    __syncwarp();
+    return;
+  }
   // literal barrier ids so that ptxas reserves 5 hardware barriers per CTA, not all 16
   switch (bar) {
     case 0: __syncthreads(); break;
@@ -226,6 +234,14 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // Cost: nothing per element; ~70 instructions per fold, i.e. ~2% of the loop.
 constexpr float kEpochWindow = 64.0f;  // range only: weights stay below 2^64, sums below 2^100
 constexpr int kFoldPeriod = 16;  // tiles (power of two)
+// Experiment kept for reproduction, OFF: every n-th element pair of a 16-bit run takes its exponential on the FMA
+// pipe (exp2_poly2: 12 instructions per pair instead of 2 MUFU). With the XU pipe 72 % busy and the FMA pipe 25 %
+// this looked like headroom; measured (interleaved A/B, all 20 regimes): n = 4: -6 %, n = 3: -5 %, n = 2: -21 %.
+// The loop is bound by instruction issue, not by the MUFU pipe: every added instruction costs its slot.
+#ifndef MVGEO_POLY_EVERY
+#define MVGEO_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = MVGEO_POLY_EVERY;
 struct SoftAcc {
   float nb;      // -ref * beta_log2e as rounded (the fold corrects with the SAME value)
   float ref_hi;  // ref + kEpochWindow / beta_log2e
@@ -295,6 +311,18 @@ __device__ __forceinline__ float ord_val(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// One map element from shared memory (32-bit shared address) as float.
+template <int DT>
+__device__ __forceinline__ float lds_elem(uint32_t addr) {
+  if constexpr (DT == MVGEO_F32) {
+    return lds32f(addr);
+  } else {
+    uint16_t b;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(b) : "r"(addr));
+    return Elem<DT>::unpack(b);
+  }
+}
+
 // Up to MVGEO_MAX_VIEWS TMA tensor maps, one per base pointer (kernel parameter, __grid_constant__): every
 // view's maps seen as a 2-D tensor [rows of 128 bytes][128 bytes].
 struct TensorMaps {
@@ -307,6 +335,18 @@ __device__ __forceinline__ void tma_load_rows(uint32_t dst_smem, const CUtensorM
                    dst_smem),
                "l"(tm), "r"(0), "r"(row), "r"(bar)
                : "memory");
+}
+
+// The same, issued by a CONSUMER lane for the slot its own warp has just emptied: `dep` is a value computed from
+// the slot's last ld.shared, so the copy cannot be issued before the warp's reads of the slot have returned.
+__device__ __forceinline__ void tma_load_rows_after(uint32_t dst_smem, const CUtensorMap* tm, int row, uint32_t bar,
+                                                    uint32_t dep) {
+  asm volatile(
+      "{\n\t.reg .b32 d;\n\tmov.b32 d, %5;\n\t"
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}" ::"r"(
+          dst_smem),
+      "l"(tm), "r"(0), "r"(row), "r"(bar), "r"(dep)
+      : "memory");
 }
 
 // G independent consumer groups per CTA (8/G warps each, own ring, own mbarriers, own named
@@ -329,8 +369,13 @@ constexpr int kRowBytes = 128;  // TMA row = two runs
 // g(x, y) = ex[x] * ey[y] built in shared memory per map (W + H exponentials, as csrc/encode.cu does) — the
 // training step's heat-map loss (nn.MSELoss, model/MvRoPose_FR3.py:846-847) and the decode of the same
 // prediction read the maps ONCE.
+// G == 8: one-warp groups that feed THEMSELVES — lane 0 re-issues the TMA copy into the slot its warp has just
+// emptied (no producer warps, no empty barriers, no named barriers: every per-map reduction is warp-wide).
+// (Self-feeding groups of 2 / 4 warps — an atomic per slot, the last warp to empty it re-issues the copy — were
+// measured too: within +-3 % of the producer warps, sign depending on the box; not kept.)
+constexpr int producer_threads(int G) { return G >= 8 ? 0 : 32 * G; }
 template <int DT, int MODE, int U, int STAGES, int G, bool MSE = false>
-__global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
+__global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_MINB)
     decode_tma_kernel(const DecodeParams p, const __grid_constant__ TensorMaps tms) {
   static_assert(!MSE || MODE == MVGEO_SOFT_NONE, "the fused loss pass decodes the hard peak only");
   static_assert(U * 16 == kRunBytes, "a run is four 16-byte chunks");
@@ -338,6 +383,7 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
   constexpr int PER = E::kPerChunk;
   constexpr int EPR = U * PER;       // elements per run
   constexpr int NW = kDecWarps / G;  // consumer warps per group
+  constexpr bool SELF = producer_threads(G) == 0;
   constexpr int NT = NW * 32;
   constexpr int kTile = NT * U;  // chunks per tile of one group
   constexpr uint32_t kTileBytes = kTile * 16;
@@ -350,6 +396,9 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
   const int rows = p.rows_per_map;                   // 64-byte runs per map
   const int n_full = rows / NT;                      // tiles without padding
   const int n_tiles = (rows + NT - 1) / NT;          // n_full or n_full + 1
+  // (A balanced assignment — only ceil(n_maps / rounds) streams active so that no stream walks a ragged last round —
+  // was measured and rejected: -1.6 % at C2, -11 % at C5. The streams left over in the last round run faster, and
+  // parallelism per SM is worth more than an even finish.)
   const int64_t step = (int64_t)gridDim.x * G;
 
   if (tid == 0) {
@@ -358,34 +407,41 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(smem_u32(&full_bar[g][s]), 1);
-        mbar_init(smem_u32(&empty_bar[g][s]), NW);
+        if (!SELF) mbar_init(smem_u32(&empty_bar[g][s]), NW);
       }
     mbar_fence_init();
   }
   __syncthreads();
 
   const int g = warp >= kDecWarps ? warp - kDecWarps : warp / NW;  // the group this warp feeds / belongs to
+  const int64_t map_first = (int64_t)blockIdx.x * G + g;
   const uint32_t ring_s = smem_u32(dyn_smem) + (uint32_t)g * STAGES * kTileBytes;
   const uint32_t full_s = smem_u32(&full_bar[g][0]);
   const uint32_t empty_s = smem_u32(&empty_bar[g][0]);
 
-  if (warp >= kDecWarps) {
+  // map (b, v, k) -> view v's tensor map and the map's first 128-byte row inside that view (maps are whole rows)
+  auto locate = [&](int64_t map, const CUtensorMap*& tm, int& row0) {
+    int v = 0;
+    int64_t local = map;
+    if (p.n_views > 1) {
+      const int64_t f = map / p.k_per_view;
+      const int64_t b = f / p.n_views;
+      v = (int)(f - b * p.n_views);
+      local = b * p.k_per_view + (map - f * p.k_per_view);
+    }
+    tm = &tms.m[v];
+    row0 = (int)(local * (rows / 2));
+  };
+
+  if (!SELF && warp >= kDecWarps) {
     // ------------------------------- producers: one warp per group (a lane suspended in try_wait
     // must not stall another group's producer), lane 0 issues ------------------------------------
     if (lane == 0) {
       int s = 0, k = 0;  // slot, and how many times the ring has wrapped
-      for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
-        // map (b, v, k) -> view v's tensor map and the map's first row inside that view
-        int v = 0;
-        int64_t local = map;
-        if (p.n_views > 1) {
-          const int64_t f = map / p.k_per_view;
-          const int64_t b = f / p.n_views;
-          v = (int)(f - b * p.n_views);
-          local = b * p.k_per_view + (map - f * p.k_per_view);
-        }
-        const CUtensorMap* tm = &tms.m[v];
-        const int row0 = (int)(local * (rows / 2));  // in 128-byte rows (maps are whole rows)
+      for (int64_t map = map_first; map < p.n_maps; map += step) {
+        const CUtensorMap* tm;
+        int row0;
+        locate(map, tm, row0);
         for (int t = 0; t < n_tiles; ++t) {
           // before re-using a slot for the k-th time, wait for the consumers' (k-1)-th release of it
           if (k > 0) mbar_wait(empty_s + 8 * s, (uint32_t)((k - 1) & 1));
@@ -433,9 +489,31 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
   const uint32_t tab_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + kDecThreads * 32 +
                          (uint32_t)g * (uint32_t)(Wp + ((p.H + 3) & ~3)) * 4;
 
+  // SELF: lane 0's copy cursor runs STAGES tiles ahead of the warp's own consumption
+  int64_t c_map = map_first;
+  int c_tile = 0, c_row = 0;
+  const CUtensorMap* c_tm = nullptr;
+  static_assert(!SELF || NW == 1, "only one-warp groups feed themselves");
+  auto issue = [&](int slot, uint32_t dep) {  // lane 0 only
+    if (c_map < p.n_maps) {
+      mbar_arrive_expect_tx(full_s + 8 * slot, kTileBytes);
+      tma_load_rows_after(ring_s + slot * kTileBytes, c_tm, c_row, full_s + 8 * slot, dep);
+      c_row += NT / 2;
+      if (++c_tile == n_tiles) {
+        c_tile = 0;
+        c_map += step;
+        if (c_map < p.n_maps) locate(c_map, c_tm, c_row);
+      }
+    }
+  };
+  if (SELF && lane == 0) {
+    if (c_map < p.n_maps) locate(c_map, c_tm, c_row);
+    for (int i = 0; i < STAGES; ++i) issue(i, 0u);
+  }
+
   int s = 0;
   uint32_t ph = 0;
-  for (int64_t map = (int64_t)blockIdx.x * G + g; map < p.n_maps; map += step) {
+  for (int64_t map = map_first; map < p.n_maps; map += step) {
     float run_max = kNegInf;
     int run_tile = gt < rows ? 0 : -1;
     SoftAcc a = {0.f, kNegInf, 0ull, 0ull, 0ull, 0ull};
@@ -479,7 +557,12 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
       // every register of the run has been consumed by the maximum: hand the slot back to the
       // producer BEFORE the exponentials, so the refill overlaps the arithmetic
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_s + 8 * s);
+      if (lane == 0) {
+        if (SELF)
+          issue(s, __float_as_uint(sm));  // refill the slot this warp has just emptied
+        else
+          mbar_arrive(empty_s + 8 * s);
+      }
       if (++s == STAGES) {
         s = 0;
         ph ^= 1;
@@ -549,8 +632,14 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
             const int gi = hf * HP + i;  // group index in the run
             float lo, hi;
             E::pair(v[gi / PPC], gi % PPC, lo, hi);
-            unpack2(fma2(pack2(lo, hi), beta2, nb2), lo, hi);
-            const f32x2 w = pack2(ex2_approx(lo), ex2_approx(hi));  // -inf padding: weight 0
+            const f32x2 t2 = fma2(pack2(lo, hi), beta2, nb2);
+            f32x2 w;
+            if (kPolyEvery > 0 && E::kBytes == 2 && gi % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1) {
+              w = exp2_poly2(t2);  // every kPolyEvery-th pair of a 16-bit run: off the MUFU pipe
+            } else {
+              unpack2(t2, lo, hi);
+              w = pack2(ex2_approx(lo), ex2_approx(hi));  // -inf padding: weight 0
+            }
             if (i == HP - 1) {
               cs[hf] = w;
             } else {
@@ -579,43 +668,52 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
     // ------------------------------ per-map epilogue (consumers of this group only) ------------
     // 1. the maximum: one redux.sync per warp on order-preserving keys, then NW values through smem
     const uint32_t wk = __reduce_max_sync(0xffffffffu, ord_key(run_max));
-    if (lane == 0) scr.key[lw] = wk;
-    group_sync<NW>(bar);
-    uint32_t mk = scr.key[0];
+    uint32_t mk = wk;
+    if (NW > 1) {
+      if (lane == 0) scr.key[lw] = wk;
+      group_sync<NW>(bar);
+      mk = scr.key[0];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) mk = max(mk, scr.key[w]);
+      for (int w = 1; w < NW; ++w) mk = max(mk, scr.key[w]);
+    }
     const float M = ord_val(mk);
 
-    // 2. the first maximal element: only threads that hold the maximum look at their winning run
-    //    (parked in shared memory by the streaming loop), lowest index wins
-    int my_idx = 0x7fffffff;
+    // 2. the first maximal element. Every thread parked its best run in shared memory; the first RUN of the
+    //    warp that holds the maximum is one redux.sync on (tile, thread), and the first maximal ELEMENT of that
+    //    run one ballot: lane j looks at element j (instead of one lane scanning its 16 / 32 elements while
+    //    the warp waits). An all -inf map parked nothing: every element is maximal and index 0 wins, below.
     const bool isn = (M != M);
-    // (an all -inf map parked nothing: every element is maximal and index 0 wins, see below)
-    if (run_tile >= 0 && M != kNegInf && (isn ? (run_max != run_max) : (__float_as_uint(run_max) == __float_as_uint(M)))) {
-      const int e0 = (run_tile * NT + gt) * EPR;
-#pragma unroll
-      for (int u = U - 1; u >= 0; --u) {  // descending: the lowest index sticks
-        const uint4 ch = lds128(cand_s + u * NT * 16);
-#pragma unroll
-        for (int j = PER - 1; j >= 0; --j) {
-          const float e = E::get(ch, j);
-          if (isn ? (e != e) : (e == M)) my_idx = e0 + u * PER + j;
-        }
+    const bool holds = run_tile >= 0 && M != kNegInf &&
+                       (isn ? (run_max != run_max) : (__float_as_uint(run_max) == __float_as_uint(M)));
+    const int first_run = __reduce_min_sync(0xffffffffu, holds ? run_tile * NT + gt : 0x7fffffff);
+    int my_idx = 0x7fffffff;
+    if (first_run != 0x7fffffff) {  // warp-uniform
+      __syncwarp();                 // the parked run was written by another lane
+      bool hit = false;
+      if (lane < EPR) {
+        const uint32_t addr = smem_u32(dyn_smem) + G * STAGES * kTileBytes +
+                              (uint32_t)(g * kTile + (lane / PER) * NT + (first_run & (NT - 1))) * 16 +
+                              (uint32_t)(lane % PER) * E::kBytes;
+        const float e = lds_elem<DT>(addr);
+        hit = isn ? (e != e) : (e == M);
       }
+      const unsigned hits = __ballot_sync(0xffffffffu, hit);
+      my_idx = first_run * EPR + __ffs(hits) - 1;
     }
-    const int wi = __reduce_min_sync(0xffffffffu, my_idx);
-    if (lane == 0) scr.idx[lw] = wi;
+    const int wi = my_idx;  // warp-uniform
+    if (NW > 1 && lane == 0) scr.idx[lw] = wi;
+    float mse_w = 0.f;
     if (MSE) {
-      const float m = warp_sum(sum2(mse_acc));
-      if (lane == 0) scr.sum[0][lw] = m;
+      mse_w = warp_sum(sum2(mse_acc));
+      if (NW > 1 && lane == 0) scr.sum[0][lw] = mse_w;
     }
     // 3. soft-arg-max sums, rescaled from the thread's reference to the true maximum. The moments are
     //    still relative to the map centre (the peak position is not reduced yet) and the thread that holds
     //    the peak carries a lever arm of hundreds of pixels that cancels in the end: the per-map
     //    reduction runs in double (a few instructions per thread and MAP, nothing per element).
     float ss = 0.f, sx = 0.f, sy = 0.f;
+    double ds = 0.0, dx = 0.0, dy = 0.0;
     if (MODE == MVGEO_SOFT_GLOBAL) {
-      double ds = 0.0, dx = 0.0, dy = 0.0;
       epoch_fold(a, tot_s);  // the last epoch
       const SoftTotals t = totals_load(tot_s);
       if (t.S > 0.0) {
@@ -628,16 +726,19 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
       ds = warp_sum_f64(ds);
       dx = warp_sum_f64(dx);
       dy = warp_sum_f64(dy);
-      if (lane == 0) {
+      if (NW > 1 && lane == 0) {
         scr.dsum[0][lw] = ds;
         scr.dsum[1][lw] = dx;
         scr.dsum[2][lw] = dy;
       }
     }
-    group_sync<NW>(bar);
-    int best = scr.idx[0];
+    int best = wi;
+    if (NW > 1) {
+      group_sync<NW>(bar);
+      best = scr.idx[0];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) best = min(best, scr.idx[w]);
+      for (int w = 1; w < NW; ++w) best = min(best, scr.idx[w]);
+    }
     if (best == 0x7fffffff) best = 0;  // all -inf map: nothing was ever parked; every element is maximal, the first wins
     const int py = best / p.W, px = best - py * p.W;
     if (MODE == MVGEO_SOFT_WINDOW) {
@@ -645,12 +746,14 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
       block_sum3<NW>(ss, sx, sy, scr, bar, lw);
     } else if (MODE == MVGEO_SOFT_GLOBAL) {
       if (gt == 0) {
-        double ds = 0.0, dx = 0.0, dy = 0.0;
+        if (NW > 1) {
+          ds = dx = dy = 0.0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {  // fixed order: deterministic
-          ds += scr.dsum[0][w];
-          dx += scr.dsum[1][w];
-          dy += scr.dsum[2][w];
+          for (int w = 0; w < NW; ++w) {  // fixed order: deterministic
+            ds += scr.dsum[0][w];
+            dx += scr.dsum[1][w];
+            dy += scr.dsum[2][w];
+          }
         }
         // shift the first moments from the map centre to the hard peak, then leave double
         ss = (float)ds;
@@ -659,9 +762,12 @@ __global__ void __launch_bounds__(kDecThreads + 32 * G, MVGEO_DEC_MINB)
       }
     }
     if (MSE && gt == 0) {
-      float m = 0.f;
+      float m = mse_w;
+      if (NW > 1) {
+        m = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) m += scr.sum[0][w];  // fixed order: deterministic
+        for (int w = 0; w < NW; ++w) m += scr.sum[0][w];  // fixed order: deterministic
+      }
       p.mse_partial[map] = m;
     }
     if (gt == 0) write_outputs(p, map, M, best, ss, sx, sy, MODE != MVGEO_SOFT_NONE);
@@ -722,6 +828,9 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 #endif
 #ifndef MVGEO_TMA_STAGES
 #define MVGEO_TMA_STAGES 4
+#endif
+#ifndef MVGEO_G8_MAX
+#define MVGEO_G8_MAX (32 * 1024)
 #endif
 #ifndef MVGEO_G4_MAX
 #define MVGEO_G4_MAX (2 * 1024 * 1024)
@@ -798,14 +907,14 @@ static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
     MVGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     int sms = 0, per_sm = 0;
     MVGEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + 32 * G, kSmemMax));
+    MVGEO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecThreads + producer_threads(G), kSmemMax));
     if (per_sm < 1) return MVGEO_EUNSUPPORTED;
     resident_ctas = sms * per_sm;
     if (dev >= 0 && dev < kMaxDevices) cache[dev].store(resident_ctas, std::memory_order_release);
   }
   const int64_t wanted = (p.n_maps + G - 1) / G;
   const unsigned grid = (unsigned)(wanted < resident_ctas ? wanted : resident_ctas);
-  kern<<<grid, kDecThreads + 32 * G, smem, st>>>(p, tms);
+  kern<<<grid, kDecThreads + producer_threads(G), smem, st>>>(p, tms);
   MVGEO_CHECK_LAUNCH();
   return MVGEO_OK;
 }
@@ -818,6 +927,7 @@ static int launch_decode(const DecodeParams& p, bool vec, int groups, cudaStream
     return MVGEO_OK;
   }
   switch (groups) {
+    case 8: return launch_persistent<DT, MODE, 8>(p, st);
     case 4: return launch_persistent<DT, MODE, 4>(p, st);
     case 2: return launch_persistent<DT, MODE, 2>(p, st);
     default: return launch_persistent<DT, MODE, 1>(p, st);
@@ -885,7 +995,7 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   // several consumer groups per CTA, one map stream each (one group's per-map epilogue overlaps the others'
   // streaming): 4 groups up to 2 MB maps (every BASELINE config; measured +3 % at C2 and +5 % at C5 over 2 / 1
   // groups), 2 up to 8 MB, one group (all 8 consumer warps on one map) beyond — a function of the map size only.
-  const int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
+  const int groups = p.map_bytes <= MVGEO_G8_MAX ? 8 : p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
     case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, groups, st);

@@ -16,6 +16,8 @@ everything between "angles / heat-maps out of the network" and "scalar loss" run
 device, with gradients:
   * GT key-points = project(FK(gt_angles))                          (mvgeo_fk + mvgeo_project)
   * L_kpt = heatmap_mse_loss(pred_maps, gt_kp, sigma=5) * 1e4       (mvgeo_heatmap_mse fwd+bwd, no GT maps materialised)
+    and, with --kp-metric fused (default), the per-step key-point pixel error of the predicted maps from the SAME read:
+    mvgeo.decode_and_mse = mvgeo_decode_mse (loss + arg-max in one pass over the maps)
   * L_fk  = fk_reproj_loss(pred_angles, gt_uv)                      (mvgeo_fk_reproj_fwd/bwd: d loss / d angles)
 DDP's gradient all-reduce over NCCL is untouched: only the trainable heads are wrapped, so only their
 gradients are bucketed. The breakdown (CUDA events, max over ranks) names the all-reduce share two ways:
@@ -77,6 +79,9 @@ def main():
     ap.add_argument("--batch", type=int, default=150, help="frames per GPU (reference: 150, Fr5_model_train.ipynb:4428-4438)")
     ap.add_argument("--head-params", type=float, default=25e6, help="trainable parameters of the stand-in heads")
     ap.add_argument("--bf16", action="store_true", help="heads under bf16 autocast (heat-maps reach the loss kernels in bf16)")
+    ap.add_argument("--kp-metric", choices=("fused", "separate", "none"), default="fused",
+                    help="key-point pixel error of the predicted maps per step: 'fused' = mvgeo.decode_and_mse (loss and "
+                         "arg-max from ONE read of the maps), 'separate' = heatmap_mse_loss + decode_heatmaps (two reads)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -121,7 +126,12 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
             maps, q = model(feats)
         e.append(ev())
-        l_kpt = mvgeo.heatmap_mse_loss(maps, gt_kp, sigma=5.0, weight=1e4)
+        if args.kp_metric == "fused":      # loss + hard decode of the same maps, read once
+            l_kpt, dec = mvgeo.decode_and_mse(maps, gt_kp, sigma=5.0, weight=1e4)
+        else:
+            l_kpt = mvgeo.heatmap_mse_loss(maps, gt_kp, sigma=5.0, weight=1e4)
+            dec = mvgeo.decode_heatmaps(maps.detach(), soft=None) if args.kp_metric == "separate" else None
+        px_err = (dec.kp_hard - gt_kp).norm(dim=-1).mean() if dec is not None else torch.zeros((), device=dev)
         l_fk, _, _, _ = mvgeo.fk_reproj_loss(chain, q.float(), rig, gt_uv, Rv, lam=1e-4)
         l_ang = nn.functional.smooth_l1_loss(q.float(), gt_q)
         loss = l_kpt + l_fk + l_ang
@@ -133,7 +143,7 @@ def main():
         e.append(ev())
         opt.step()
         e.append(ev())
-        return e, (loss.detach(), l_kpt.detach(), l_fk.detach())
+        return e, (loss.detach(), l_kpt.detach(), l_fk.detach(), px_err)
 
     def timed(n, sync=True):
         rows, hist = [], []
@@ -171,6 +181,22 @@ def main():
         torch.cuda.synchronize(dev)
         lk_f.append(a.elapsed_time(b))
         lk_b.append(b.elapsed_time(c))
+    # the same forward with the per-step key-point metric: one read (fused) against two (MSE, then decode)
+    fwd_variants = {}
+    for name in ("mse_only", "mse_then_decode", "fused_decode_mse"):
+        ts = []
+        for _ in range(10):
+            a = ev()
+            if name == "fused_decode_mse":
+                mvgeo.decode_and_mse(maps0, gt_kp, sigma=5.0, weight=1e4)
+            else:
+                mvgeo.heatmap_mse_loss(maps0, gt_kp, sigma=5.0, weight=1e4)
+                if name == "mse_then_decode":
+                    mvgeo.decode_heatmaps(maps0, soft=None)
+            b = ev()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        fwd_variants[name] = statistics.median(ts)
     ar_ms = None
     if world > 1:  # a stand-alone all-reduce of the trainable gradient bytes
         flat = torch.zeros(n_train, device=dev)
@@ -205,7 +231,10 @@ def main():
                           "standalone_busbw_gbs": (4 * n_train * 2 * (world - 1) / world / (vals[14] * 1e-3) / 1e9) if vals[14] else None},
             "loss_kernels": {"fwd_ms": vals[12], "bwd_ms": vals[13], "share_of_step": (vals[12] + vals[13]) / p[5],
                              "pred_map_bytes": map_bytes,
-                             "fwd_gbs": map_bytes / (vals[12] * 1e-3) / 1e9, "bwd_gbs": 2 * map_bytes / (vals[13] * 1e-3) / 1e9},
+                             "fwd_gbs": map_bytes / (vals[12] * 1e-3) / 1e9, "bwd_gbs": 2 * map_bytes / (vals[13] * 1e-3) / 1e9,
+                             "kpt_fwd_ms_rank0": fwd_variants,
+                             "kpt_fwd_gbs_one_read_rank0": map_bytes / (fwd_variants["fused_decode_mse"] * 1e-3) / 1e9},
+            "kp_metric": args.kp_metric, "kp_px_error_first_last": [first[3], last[3]],
             "loss_first": first, "loss_last": last}))
     if world > 1:
         dist.barrier()

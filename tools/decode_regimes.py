@@ -17,6 +17,8 @@ SHAPES = {  # name: (n_maps, H, W, dtype)
     "native32": (2048 * 3 * 7, 128, 128, torch.float32),   # reference-native map, fp32: 2.8 GB
     "native16": (4096 * 3 * 7, 128, 128, torch.bfloat16),  # reference-native map under bf16 autocast: 2.8 GB
     "c5": (128 * 8 * 8, 480, 640, torch.bfloat16),         # BASELINE config 5: 5.03 GB
+    "c2b": (1024 * 4 * 7, 240, 320, torch.bfloat16),       # a C2 launch that leaves the last round of map streams ragged
+    "c5b": (128 * 8 * 7, 480, 640, torch.bfloat16),        # the same for C5 (6.05 rounds of 1,184 streams)
 }
 BETAS = (5.0, 15.0, 30.0, 100.0, 400.0)
 AMPS = (0.05, 0.3, 1.0)
@@ -48,6 +50,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "2025_icra_multi_view_robot_pose_estimation_b200", "libmvgeo.so"))
     ap.add_argument("--tag", default="r02")
+    ap.add_argument("--lib-b", default="", help="a second build to time INTERLEAVED with --lib (A, B, A, B, ...: same clocks)")
+    ap.add_argument("--tag-b", default="b")
     ap.add_argument("--shapes", default="c2,native32,native16")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "decode_regimes.jsonl"))
     ap.add_argument("--only", default="", help="dist:amp:beta — run a single cell (for ncu)")
@@ -55,6 +59,7 @@ def main():
     ap.add_argument("--mode", type=int, default=1, help="1 global (default), 2 window, 0 none")
     a = ap.parse_args()
     lib = bind(a.lib)
+    libs = [(a.tag, lib)] + ([(a.tag_b, bind(a.lib_b))] if a.lib_b else [])
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream().cuda_stream
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -88,20 +93,30 @@ def main():
                 if only and float(only[2]) != beta:
                     continue
 
-                def run():
-                    rc = lib.mvgeo_decode(maps.data_ptr(), DT[dtype], n_maps, H, W, 1.0, 1.0, a.mode, beta, 3, 0, 1, 1, 0,
-                                          idx.data_ptr(), peak.data_ptr(), score.data_ptr(), kph.data_ptr(),
-                                          kps.data_ptr(), st)
+                def run(l=lib):
+                    rc = l.mvgeo_decode(maps.data_ptr(), DT[dtype], n_maps, H, W, 1.0, 1.0, a.mode, beta, 3, 0, 1, 1, 0,
+                                        idx.data_ptr(), peak.data_ptr(), score.data_ptr(), kph.data_ptr(),
+                                        kps.data_ptr(), st)
                     assert rc == 0, rc
                 for _ in range(3):
-                    run()
+                    for _, l in libs:
+                        run(l)
                 torch.cuda.synchronize()
-                ts = []
+                tsl = {t: [] for t, _ in libs}
                 for _ in range(a.iters):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(); run(); e1.record()
-                    torch.cuda.synchronize()
-                    ts.append(e0.elapsed_time(e1))
+                    for t, l in reversed(libs):  # the first library runs last: its outputs are the ones checked below
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(); run(l); e1.record()
+                        torch.cuda.synchronize()
+                        tsl[t].append(e0.elapsed_time(e1))
+                for t, _ in libs[1:]:
+                    mb = statistics.median(tsl[t])
+                    rec = {"lib": t, "shape": name, "n_maps": n_maps, "H": H, "W": W, "dtype": str(dtype).split(".")[1],
+                           "dist": dist, "amp": amp, "beta": beta, "mode": a.mode, "us": mb * 1e3, "gbs": nbytes / mb / 1e6,
+                           "gbs_best": nbytes / min(tsl[t]) / 1e6, "soft_err_map_px": 0.0, "interleaved_with": a.tag}
+                    print(json.dumps(rec), flush=True)
+                    fout.write(json.dumps(rec) + "\n")
+                ts = tsl[a.tag]
                 med = statistics.median(ts)
                 ns = min(n_maps, 96)
                 rs, ri = ref_soft(maps[:ns], beta)

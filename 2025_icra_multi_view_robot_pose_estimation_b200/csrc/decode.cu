@@ -249,26 +249,35 @@ struct SoftAcc {
   f32x2 sj;              // sum w i, i = index of the element's 2-element group inside its chunk
 };
 
-// Per-thread, per-map totals over the finished epochs: S, SX, SY relative to reference nb (32 bytes in
-// shared memory; touched only by the fold).
+// Per-thread, per-map totals over the finished epochs: S, SX, SY relative to reference nb (32 bytes per thread in
+// shared memory, touched only by the fold). Stored as arrays over the NT threads of a group — S[NT], SX[NT],
+// SY[NT] (double), nb[NT] (float) — so that a warp's accesses are consecutive words: no bank conflicts.
 struct SoftTotals {
   double S, SX, SY;
   float nb;  // +inf: empty
 };
-__device__ __forceinline__ void totals_store(uint32_t addr, const SoftTotals& t) {
-  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(t.S), "d"(t.SX) : "memory");
-  asm volatile("st.shared.f64 [%0+16], %1;" ::"r"(addr), "d"(t.SY) : "memory");
-  asm volatile("st.shared.f32 [%0+24], %1;" ::"r"(addr), "f"(t.nb) : "memory");
+// the group's block is aligned to its size (NT * 32): thread index = (addr mod NT*8) / 8, nb[] starts at +NT*24
+template <int NT>
+__device__ __forceinline__ uint32_t totals_nb_addr(uint32_t addr) { return addr - ((addr & (NT * 8 - 1)) >> 1); }
+template <int NT>
+__device__ __forceinline__ void totals_store(uint32_t addr, const SoftTotals& t) {  // addr = group base + 8 * thread
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(t.S) : "memory");
+  asm volatile("st.shared.f64 [%0+%2], %1;" ::"r"(addr), "d"(t.SX), "n"(NT * 8) : "memory");
+  asm volatile("st.shared.f64 [%0+%2], %1;" ::"r"(addr), "d"(t.SY), "n"(NT * 16) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(totals_nb_addr<NT>(addr)), "f"(t.nb), "n"(NT * 24) : "memory");
 }
+template <int NT>
 __device__ __forceinline__ SoftTotals totals_load(uint32_t addr) {
   SoftTotals t;
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(t.S), "=d"(t.SX) : "r"(addr));
-  asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(t.SY) : "r"(addr));
-  asm volatile("ld.shared.f32 %0, [%1+24];" : "=f"(t.nb) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t.S) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(t.SX) : "r"(addr), "n"(NT * 8));
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(t.SY) : "r"(addr), "n"(NT * 16));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(t.nb) : "r"(totals_nb_addr<NT>(addr)), "n"(NT * 24));
   return t;
 }
 // Fold the epoch held in `a` into the totals (common reference = the higher of the two, so the
 // scale factor is <= 1 and can only underflow to a truly negligible 0), and clear the epoch.
+template <int NT>
 __device__ __forceinline__ void epoch_fold(SoftAcc& a, uint32_t totals_addr) {
   const float ts = sum2(a.s);
   if (ts > 0.f) {  // an empty epoch (or one poisoned by +inf - +inf) adds nothing
@@ -282,7 +291,7 @@ __device__ __forceinline__ void epoch_fold(SoftAcc& a, uint32_t totals_addr) {
     const double SX = ((double)h0 + (double)h1) + 2.0 * ((double)j0 + (double)j1) + (double)s_odd;
     unpack2(a.sy, h0, h1);
     const double SY = (double)h0 + (double)h1;
-    SoftTotals t = totals_load(totals_addr);
+    SoftTotals t = totals_load<NT>(totals_addr);
     if (a.nb <= t.nb) {  // the epoch's reference is the higher one (nb = -ref*beta'): bring the totals to it
       const double f = (double)ex2_approx(a.nb - t.nb);  // empty totals: nb = +inf -> f = 0
       t.S = t.S * f + S;
@@ -295,7 +304,7 @@ __device__ __forceinline__ void epoch_fold(SoftAcc& a, uint32_t totals_addr) {
       t.SX += SX * f;
       t.SY += SY * f;
     }
-    totals_store(totals_addr, t);
+    totals_store<NT>(totals_addr, t);
   }
   a.s = a.sx = a.sy = a.sj = 0ull;
 }
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
   // epilogue finds the first maximal element there, not in global memory) ...
   const uint32_t cand_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + (uint32_t)(g * kTile + gt) * 16;
   // ... and every thread's per-map soft-arg-max totals (32 bytes each)
-  const uint32_t tot_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + (uint32_t)(g * NT + gt) * 32;
+  const uint32_t tot_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + G * kTileBytes + (uint32_t)(g * NT * 32 + gt * 8);
 
   // Soft-arg-max geometry: coordinates are relative to the map centre; from one tile to the next a
   // run advances by (step_y rows, step_x columns) with at most one row wrap.
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
     float run_max = kNegInf;
     int run_tile = gt < rows ? 0 : -1;
     SoftAcc a = {0.f, kNegInf, 0ull, 0ull, 0ull, 0ull};
-    if (MODE == MVGEO_SOFT_GLOBAL) totals_store(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
+    if (MODE == MVGEO_SOFT_GLOBAL) totals_store<NT>(tot_s, SoftTotals{0.0, 0.0, 0.0, __int_as_float(0x7f800000)});
     int ix = x00, iy = y00;
     f32x2 mse_acc = 0ull;
     if (MSE) {
@@ -611,7 +620,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
         // (bounds the f32 rounding of the long tail after a peak, wherever in the map the peak sits).
         const bool climb = sm > a.ref_hi;
         if (climb || (t & (kFoldPeriod - 1)) == kFoldPeriod - 1) {
-          epoch_fold(a, tot_s);
+          epoch_fold<NT>(a, tot_s);
           if (climb) {
             a.nb = -sm * p.beta_log2e;
             a.ref_hi = sm + window;
@@ -714,8 +723,8 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
     float ss = 0.f, sx = 0.f, sy = 0.f;
     double ds = 0.0, dx = 0.0, dy = 0.0;
     if (MODE == MVGEO_SOFT_GLOBAL) {
-      epoch_fold(a, tot_s);  // the last epoch
-      const SoftTotals t = totals_load(tot_s);
+      epoch_fold<NT>(a, tot_s);  // the last epoch
+      const SoftTotals t = totals_load<NT>(tot_s);
       if (t.S > 0.0) {
         // 2^((ref - M) beta') formed with the rounded nb the weights were formed with: its rounding cancels
         const double r = (double)ex2_approx(fmaf(-M, p.beta_log2e, -t.nb));

@@ -372,8 +372,7 @@ __device__ __forceinline__ void tma_load_rows_after(uint32_t dst_smem, const CUt
 #ifndef MVGEO_DEC_MINB
 #define MVGEO_DEC_MINB 2  // measured: 2 CTAs/SM without a register cap beat 3 CTAs/SM at 64 registers (spills)
 #endif
-constexpr int kRunBytes = 64;   // bytes one thread owns per tile
-constexpr int kRowBytes = 128;  // TMA row = two runs
+constexpr int kRowBytes = 128;  // TMA row; a thread's run is a whole row (U = 8 chunks) or half of one (U = 4)
 // MSE: the same pass also accumulates sum (pred - g)^2 per map against the separable Gaussian target
 // g(x, y) = ex[x] * ey[y] built in shared memory per map (W + H exponentials, as csrc/encode.cu does) — the
 // training step's heat-map loss (nn.MSELoss, model/MvRoPose_FR3.py:846-847) and the decode of the same
@@ -387,7 +386,8 @@ template <int DT, int MODE, int U, int STAGES, int G, bool MSE = false>
 __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_MINB)
     decode_tma_kernel(const DecodeParams p, const __grid_constant__ TensorMaps tms) {
   static_assert(!MSE || MODE == MVGEO_SOFT_NONE, "the fused loss pass decodes the hard peak only");
-  static_assert(U * 16 == kRunBytes, "a run is four 16-byte chunks");
+  static_assert(U == 4 || U == 8, "a run is half a 128-byte TMA row or a whole one");
+  constexpr int RPR = kRowBytes / (U * 16);  // runs per TMA row
   using E = Elem<DT>;
   constexpr int PER = E::kPerChunk;
   constexpr int EPR = U * PER;       // elements per run
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
       local = b * p.k_per_view + (map - f * p.k_per_view);
     }
     tm = &tms.m[v];
-    row0 = (int)(local * (rows / 2));
+    row0 = (int)(local * (rows / RPR));
   };
 
   if (!SELF && warp >= kDecWarps) {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
           // the box is always delivered whole: rows past the end of the tensor arrive as zeros, rows of the
           // NEXT map as that map's data — the consumers mask both (they know how many runs the map has)
           mbar_arrive_expect_tx(full_s + 8 * s, kTileBytes);
-          tma_load_rows(ring_s + s * kTileBytes, tm, row0 + t * (NT / 2), full_s + 8 * s);
+          tma_load_rows(ring_s + s * kTileBytes, tm, row0 + t * (NT / RPR), full_s + 8 * s);
           if (++s == STAGES) {
             s = 0;
             ++k;
@@ -473,9 +473,9 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
   const int lw = gt >> 5;
   const int bar = 1 + g;
   BlockScratch& scr = sc[g];
-  const uint32_t my_s = ring_s + (uint32_t)(gt >> 1) * kRowBytes;  // this thread's 128-byte row in slot 0
-  // 128-byte swizzle: 16-byte chunk c of row r lives at c ^ (r & 7); this thread's chunk u is c = 4 (gt & 1) + u
-  const uint32_t sw = (uint32_t)((((gt & 1) << 2) ^ ((gt >> 1) & 7)) << 4);
+  const uint32_t my_s = ring_s + (uint32_t)(gt / RPR) * kRowBytes;  // this thread's 128-byte row in slot 0
+  // 128-byte swizzle: 16-byte chunk c of row r lives at c ^ (r & 7); this thread's chunk u is c = U (gt % RPR) + u
+  const uint32_t sw = (uint32_t)((((gt % RPR) * U) ^ ((gt / RPR) & 7)) << 4);
   // behind the rings: the raw chunks of every thread's best run so far ([g][u][gt], 16 KB per CTA: the
   // epilogue finds the first maximal element there, not in global memory) ...
   const uint32_t cand_s = smem_u32(dyn_smem) + G * STAGES * kTileBytes + (uint32_t)(g * kTile + gt) * 16;
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
     if (c_map < p.n_maps) {
       mbar_arrive_expect_tx(full_s + 8 * slot, kTileBytes);
       tma_load_rows_after(ring_s + slot * kTileBytes, c_tm, c_row, full_s + 8 * slot, dep);
-      c_row += NT / 2;
+      c_row += NT / RPR;
       if (++c_tile == n_tiles) {
         c_tile = 0;
         c_map += step;
@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
         // accumulator that holds the peak's mass never takes more than kFoldPeriod background tiles on top
         // (bounds the f32 rounding of the long tail after a peak, wherever in the map the peak sits).
         const bool climb = sm > a.ref_hi;
-        if (climb || (t & (kFoldPeriod - 1)) == kFoldPeriod - 1) {
+        constexpr int kFoldTiles = kFoldPeriod * 4 / U;  // the same number of elements per fold for either run length
+        if (climb || (t & (kFoldTiles - 1)) == kFoldTiles - 1) {
           epoch_fold<NT>(a, tot_s);
           if (climb) {
             a.nb = -sm * p.beta_log2e;
@@ -698,16 +699,27 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
     int my_idx = 0x7fffffff;
     if (first_run != 0x7fffffff) {  // warp-uniform
       __syncwarp();                 // the parked run was written by another lane
-      bool hit = false;
-      if (lane < EPR) {
-        const uint32_t addr = smem_u32(dyn_smem) + G * STAGES * kTileBytes +
-                              (uint32_t)(g * kTile + (lane / PER) * NT + (first_run & (NT - 1))) * 16 +
-                              (uint32_t)(lane % PER) * E::kBytes;
-        const float e = lds_elem<DT>(addr);
-        hit = isn ? (e != e) : (e == M);
+      // lane j looks at elements j, j + 32, ... of that run (a run holds 16 / 32 / 64 elements)
+      unsigned hits = 0;
+      int base = 0;
+#pragma unroll
+      for (int k = 0; k < EPR; k += 32) {
+        bool hit = false;
+        const int j = k + lane;
+        if (j < EPR) {
+          const uint32_t addr = smem_u32(dyn_smem) + G * STAGES * kTileBytes +
+                                (uint32_t)(g * kTile + (j / PER) * NT + (first_run & (NT - 1))) * 16 +
+                                (uint32_t)(j % PER) * E::kBytes;
+          const float e = lds_elem<DT>(addr);
+          hit = isn ? (e != e) : (e == M);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hits == 0 && b != 0) {
+          hits = b;
+          base = k;
+        }
       }
-      const unsigned hits = __ballot_sync(0xffffffffu, hit);
-      my_idx = first_run * EPR + __ffs(hits) - 1;
+      my_idx = first_run * EPR + base + __ffs(hits) - 1;
     }
     const int wi = my_idx;  // warp-uniform
     if (NW > 1 && lane == 0) scr.idx[lw] = wi;
@@ -831,13 +843,11 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
   if (tid == 0) write_outputs(p, map, M, best, s, sx, sy, MODE != MVGEO_SOFT_NONE);
 }
 
-// Streaming-kernel configuration: tile = 256*kTmaU chunks over the CTA's groups, kTmaStages-deep ring.
-#ifndef MVGEO_TMA_U
-#define MVGEO_TMA_U 4
-#endif
-#ifndef MVGEO_TMA_STAGES
-#define MVGEO_TMA_STAGES 4
-#endif
+// Streaming-kernel configuration. A thread owns a run of U 16-byte chunks per tile: U = 8 (a whole 128-byte TMA row,
+// 2-stage ring of 8 KB / 4 KB tiles) wherever the image rows hold whole 128-byte runs — the per-tile fixed costs
+// (mbarrier wait, maximum finish, parking, position, fold test, slot hand-back: ~85 of 218 instructions) are paid
+// per 128 bytes instead of 64: +6 % at C2, +8 % at C5, +10 % on 32 KB maps; U = 4 (half a row, 4-stage ring)
+// for global soft mode / the fused loss pass on maps whose rows hold whole 64-byte runs only.
 #ifndef MVGEO_G8_MAX
 #define MVGEO_G8_MAX (32 * 1024)
 #endif
@@ -847,10 +857,9 @@ __global__ void __launch_bounds__(kDecThreads) decode_scalar_kernel(const Decode
 #ifndef MVGEO_G2_MAX
 #define MVGEO_G2_MAX (8 * 1024 * 1024)
 #endif
-constexpr int kTmaU = MVGEO_TMA_U;
-constexpr int kTmaStages = MVGEO_TMA_STAGES;
+constexpr int ring_stages(int U) { return U == 8 ? 2 : 4; }
 // per CTA: the rings, one tile of parked candidate runs and the 32-byte soft-arg-max totals per thread
-constexpr size_t kRingBytes = (size_t)(kTmaStages + 1) * kTmaU * kDecThreads * 16 + (size_t)kDecThreads * 32;
+constexpr size_t ring_bytes(int U) { return (size_t)(ring_stages(U) + 1) * U * kDecThreads * 16 + (size_t)kDecThreads * 32; }
 constexpr int kMaxDevices = 64;
 
 
@@ -877,7 +886,7 @@ static int build_tensor_maps(const DecodeParams& p, int box_rows, TensorMaps& tm
   if (!enc) return MVGEO_EUNSUPPORTED;
   memset(&tms, 0, sizeof(tms));
   const int64_t maps_per_view = p.n_views == 1 ? p.n_maps : p.n_maps / p.n_views;
-  const uint64_t rows_total = (uint64_t)maps_per_view * (uint64_t)(p.rows_per_map / 2);
+  const uint64_t rows_total = (uint64_t)maps_per_view * (uint64_t)(p.map_bytes / kRowBytes);
   if (rows_total > 0x7fffffffull) return MVGEO_EUNSUPPORTED;  // TMA coordinates are 32-bit signed (137 GB per view)
   for (int v = 0; v < p.n_views; ++v) {
     const cuuint64_t gdim[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)rows_total};
@@ -894,19 +903,19 @@ static int build_tensor_maps(const DecodeParams& p, int box_rows, TensorMaps& tm
 
 constexpr size_t kMseTableMax = 16 * 1024;  // shared memory of the fused loss pass's Gaussian tables (2 CTAs/SM still fit)
 
-template <int DT, int MODE, int G, bool MSE = false>
+template <int DT, int MODE, int G, int U, bool MSE = false>
 static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
-  auto kern = decode_tma_kernel<DT, MODE, kTmaU, kTmaStages, G, MSE>;
+  auto kern = decode_tma_kernel<DT, MODE, U, ring_stages(U), G, MSE>;
   // Resident-wave size per (instantiation, device): a pure function of its key, cached because the
   // occupancy query costs microseconds on a latency-bound call. The dynamic shared-memory opt-in is
   // set to the SAME constant by every caller (the ring never changes size), so concurrent callers
   // cannot disturb one another; a racing thread recomputes and stores the same value.
-  constexpr size_t kSmemMax = kRingBytes + (MSE ? kMseTableMax : 0);
+  constexpr size_t kSmemMax = ring_bytes(U) + (MSE ? kMseTableMax : 0);
   const size_t smem = kSmemMax;  // constant per instantiation: the cached occupancy is exact
   if (MSE && (size_t)G * (((p.W + 3) & ~3) + ((p.H + 3) & ~3)) * 4 > kMseTableMax)
     return MVGEO_EUNSUPPORTED;  // very wide / tall maps: use the two separate passes
   TensorMaps tms;
-  const int rc = build_tensor_maps(p, kDecThreads / G / 2, tms);
+  const int rc = build_tensor_maps(p, kDecThreads / G * (U * 16) / kRowBytes, tms);
   if (rc) return rc;
   static std::atomic<int> cache[kMaxDevices];
   int dev = 0;
@@ -928,27 +937,36 @@ static int launch_persistent(const DecodeParams& p, cudaStream_t st) {
   return MVGEO_OK;
 }
 
+template <int DT, int MODE, int U>
+static int launch_groups(const DecodeParams& p, int groups, cudaStream_t st) {
+  switch (groups) {
+    case 8: return launch_persistent<DT, MODE, 8, U>(p, st);
+    case 4: return launch_persistent<DT, MODE, 4, U>(p, st);
+    case 2: return launch_persistent<DT, MODE, 2, U>(p, st);
+    default: return launch_persistent<DT, MODE, 1, U>(p, st);
+  }
+}
+
+// run_chunks: 16-byte chunks per thread and tile of the streaming kernel (8 or 4), 0 = the element-wise kernel
 template <int DT, int MODE>
-static int launch_decode(const DecodeParams& p, bool vec, int groups, cudaStream_t st) {
-  if (!vec) {
+static int launch_decode(const DecodeParams& p, int run_chunks, int groups, cudaStream_t st) {
+  if (run_chunks == 0) {
     decode_scalar_kernel<DT, MODE><<<(unsigned)p.n_maps, kDecThreads, 0, st>>>(p);
     MVGEO_CHECK_LAUNCH();
     return MVGEO_OK;
   }
-  switch (groups) {
-    case 8: return launch_persistent<DT, MODE, 8>(p, st);
-    case 4: return launch_persistent<DT, MODE, 4>(p, st);
-    case 2: return launch_persistent<DT, MODE, 2>(p, st);
-    default: return launch_persistent<DT, MODE, 1>(p, st);
+  if constexpr (MODE == MVGEO_SOFT_GLOBAL) {  // only the online soft-arg-max needs runs that stay inside an image row
+    if (run_chunks == 4) return launch_groups<DT, MODE, 4>(p, groups, st);
   }
+  return launch_groups<DT, MODE, 8>(p, groups, st);
 }
 
 template <int DT>
-static int dispatch_mode(const DecodeParams& p, int mode, bool vec, int groups, cudaStream_t st) {
+static int dispatch_mode(const DecodeParams& p, int mode, int run_chunks, int groups, cudaStream_t st) {
   switch (mode) {
-    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, vec, groups, st);
-    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, vec, groups, st);
-    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, vec, groups, st);
+    case MVGEO_SOFT_NONE: return launch_decode<DT, MVGEO_SOFT_NONE>(p, run_chunks, groups, st);
+    case MVGEO_SOFT_GLOBAL: return launch_decode<DT, MVGEO_SOFT_GLOBAL>(p, run_chunks, groups, st);
+    case MVGEO_SOFT_WINDOW: return launch_decode<DT, MVGEO_SOFT_WINDOW>(p, run_chunks, groups, st);
   }
   return MVGEO_EINVAL;
 }
@@ -973,13 +991,15 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.map_bytes = (int64_t)H * W * esize;
   // Work decomposition is a function of the map shape only (never of n_maps or the data), so results
   // are bit-identical however the frames are sharded across GPUs.
-  // streaming kernel: maps made of whole 64-byte runs; global soft mode: runs that never straddle two rows
-  bool vec = (p.map_bytes % kRowBytes == 0);
-  if (soft_mode == MVGEO_SOFT_GLOBAL && (W * esize) % kRunBytes != 0) vec = false;
+  // streaming kernel: maps made of whole 128-byte TMA rows, every thread a run of 128 bytes per tile; global soft
+  // mode: runs that never straddle two image rows — 128-byte runs if the rows allow, else 64-byte runs
+  int run_chunks = (p.map_bytes % kRowBytes == 0) ? 8 : 0;
+  if (run_chunks && soft_mode == MVGEO_SOFT_GLOBAL)
+    run_chunks = (W * esize) % 128 == 0 ? 8 : (W * esize) % 64 == 0 ? 4 : 0;
   for (int v = 0; v < n_views; ++v) {
     if (!view_maps[v]) return MVGEO_ENULL;
     p.view_base[v] = view_maps[v];
-    if (reinterpret_cast<uintptr_t>(view_maps[v]) & 15) vec = false;
+    if (reinterpret_cast<uintptr_t>(view_maps[v]) & 15) run_chunks = 0;
   }
   p.n_views = n_views;
   p.k_per_view = k_per_view;
@@ -1000,16 +1020,16 @@ static int decode_impl(const void* const* view_maps, int n_views, int k_per_view
   p.score = score;
   p.kp_hard = kp_hard;
   p.kp_soft = kp_soft;
-  p.rows_per_map = vec ? (int)(p.map_bytes / kRunBytes) : 0;
+  p.rows_per_map = run_chunks ? (int)(p.map_bytes / (run_chunks * 16)) : 0;
   // several consumer groups per CTA, one map stream each (one group's per-map epilogue overlaps the others'
   // streaming): 4 groups up to 2 MB maps (every BASELINE config; measured +3 % at C2 and +5 % at C5 over 2 / 1
   // groups), 2 up to 8 MB, one group (all 8 consumer warps on one map) beyond — a function of the map size only.
   const int groups = p.map_bytes <= MVGEO_G8_MAX ? 8 : p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
-    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, vec, groups, st);
-    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, vec, groups, st);
-    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, vec, groups, st);
+    case MVGEO_F32: return dispatch_mode<MVGEO_F32>(p, soft_mode, run_chunks, groups, st);
+    case MVGEO_BF16: return dispatch_mode<MVGEO_BF16>(p, soft_mode, run_chunks, groups, st);
+    case MVGEO_F16: return dispatch_mode<MVGEO_F16>(p, soft_mode, run_chunks, groups, st);
   }
   return MVGEO_EINVAL;
 }
@@ -1030,12 +1050,15 @@ extern "C" int mvgeo_decode(const void* maps, int dtype, int64_t n_maps, int H, 
 namespace mvgeo {
 int finish_mse(const float* partial, int64_t n_maps, double N, float weight, float* loss, cudaStream_t st);  // encode.cu
 
+// the fused loss pass keeps 64-byte runs: its Gaussian tables (16 KB) and the 128-byte-run ring do not fit twice per SM
+constexpr int kMseU = 4;
 template <int DT>
 static int launch_decode_mse(const DecodeParams& p, int groups, cudaStream_t st) {
   switch (groups) {
-    case 4: return launch_persistent<DT, MVGEO_SOFT_NONE, 4, true>(p, st);
-    case 2: return launch_persistent<DT, MVGEO_SOFT_NONE, 2, true>(p, st);
-    default: return launch_persistent<DT, MVGEO_SOFT_NONE, 1, true>(p, st);
+    case 8: return launch_persistent<DT, MVGEO_SOFT_NONE, 8, kMseU, true>(p, st);
+    case 4: return launch_persistent<DT, MVGEO_SOFT_NONE, 4, kMseU, true>(p, st);
+    case 2: return launch_persistent<DT, MVGEO_SOFT_NONE, 2, kMseU, true>(p, st);
+    default: return launch_persistent<DT, MVGEO_SOFT_NONE, 1, kMseU, true>(p, st);
   }
 }
 }  // namespace mvgeo
@@ -1051,7 +1074,7 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   const int esize = dtype == MVGEO_F32 ? 4 : 2;
   // the fused pass is the streaming kernel only: 16-byte aligned maps of whole 128-byte TMA rows whose image rows
   // hold whole 64-byte runs
-  if ((reinterpret_cast<uintptr_t>(maps) & 15) || (W * esize) % kRunBytes != 0 || ((int64_t)H * W * esize) % kRowBytes != 0)
+  if ((reinterpret_cast<uintptr_t>(maps) & 15) || (W * esize) % (kMseU * 16) != 0 || ((int64_t)H * W * esize) % kRowBytes != 0)
     return MVGEO_EUNSUPPORTED;
   DecodeParams p = {};
   p.view_base[0] = maps;
@@ -1061,7 +1084,7 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   p.map_bytes = (int64_t)H * W * esize;
   p.H = H;
   p.W = W;
-  p.rows_per_map = (int)(p.map_bytes / kRunBytes);
+  p.rows_per_map = (int)(p.map_bytes / (kMseU * 16));
   p.scale_x = scale_x;
   p.scale_y = scale_y;
   p.apply_sigmoid = apply_sigmoid;
@@ -1074,7 +1097,7 @@ extern "C" int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int
   p.mse_kp = kp_target;
   p.mse_k = kLog2e / (2.0f * sigma * sigma);
   p.mse_partial = partial;
-  int groups = p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
+  int groups = p.map_bytes <= MVGEO_G8_MAX ? 8 : p.map_bytes <= MVGEO_G4_MAX ? 4 : (p.map_bytes <= MVGEO_G2_MAX ? 2 : 1);
   // every consumer group holds its own pair of Gaussian tables: fewer groups for wide / tall maps (shape only)
   while (groups > 1 && (size_t)groups * (((W + 3) & ~3) + ((H + 3) & ~3)) * 4 > kMseTableMax) groups >>= 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -922,6 +922,41 @@ def test_decode_many_maps_per_cta_vs_oracle(mv, n_maps, HW, dtype):
     assert torch.equal(r.kp_soft, r2.kp_soft) and torch.equal(r.idx, r2.idx)
 
 
+@pytest.mark.parametrize("HW,dtype", [((40, 64), torch.bfloat16), ((10, 32), torch.float32), ((128, 128), torch.float16),
+                                      ((24, 96), torch.bfloat16), ((64, 128), torch.float32)])
+@pytest.mark.parametrize("n_maps", [1, 3, 9, 100, 2369])
+def test_decode_one_warp_streams_small_maps(mv, HW, dtype, n_maps):
+    """Maps up to 32 KB run 8 one-warp map streams per CTA that feed themselves (lane 0 re-issues the TMA copy into
+    the slot its warp has just emptied). Fewer maps than streams (idle warps issue nothing), maps of 2.5 / 0.6 / 16
+    tiles (a ragged last tile shows the NEXT map's rows and must be masked), one more map than the resident wave has
+    streams, every soft mode, NaN / +-inf / all -inf maps: everything against the oracle."""
+    H, W = HW
+    rng = np.random.default_rng(1000 + n_maps)
+    a, _ = _blob_maps(rng, n_maps, H, W, sigma=2.5, noise=0.05)
+    a[::5] = rng.random((len(a[::5]), H, W)).astype(np.float32)            # flat noise
+    a[::9] = np.round(a[::9] * 4) / 4                                        # ties
+    if n_maps >= 9:
+        a[2, H - 1, W - 1] = 5.0
+        a[4] = -np.inf
+        a[6, H // 2, 3] = np.nan
+        a[7, 1, 1] = np.inf
+    t, seen = _as_dtype(a, dtype)
+    plain = np.ones(n_maps, dtype=bool)
+    if n_maps >= 9:
+        plain[[4, 6, 7]] = False                                             # soft key-point of a non-finite map: below
+    for soft in (None, "window", "global"):
+        r = mv.decode_heatmaps(t, (H * 3, W * 4), soft=soft, beta=20.0, window_radius=2)
+        np.testing.assert_array_equal(r.idx.cpu().numpy(), O.argmax_first(seen)[0])
+        d = O.decode(seen[plain], 4.0, 3.0, soft or "none", beta=20.0, radius=2)
+        np.testing.assert_array_equal(_to_np32(r.kp_hard)[plain], d["kp_hard"])
+        if soft:
+            got = _to_np32(r.kp_soft)
+            assert np.abs(got[plain] - d["kp_soft"]).max() < 1e-3
+            if n_maps >= 9:
+                assert np.all(np.isnan(got[6]))                              # NaN peak -> NaN
+                np.testing.assert_array_equal(got[4], [0, 0])                # all -inf -> hard peak (index 0)
+
+
 def test_decode_global_mode_beyond_19_mb_and_odd_rows(mv):
     """Maps of any size stream through the online soft-arg-max (round 1 refused global mode above ~19 MB), and
     rows that do not hold a whole number of 16-byte chunks take the generic kernel."""

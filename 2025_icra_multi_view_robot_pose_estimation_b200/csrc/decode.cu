@@ -8,10 +8,11 @@
 // distribution (algorithmic bytes per map = H*W*sizeof(dtype); outputs are 28 B per map). Design:
 //   * PERSISTENT kernel: (SMs x resident CTAs) CTAs, each walking maps blockIdx.x, +gridDim.x, ...
 //     One elected producer lane per map stream issues 2-D tensor-map TMA loads (cp.async.bulk.tensor.2d,
-//     SASS UTMALDG.2D; the maps are described as a tensor of 128-byte rows) of 16 KB / G tiles into a
-//     4-stage shared-memory ring with full/empty mbarriers, written with the 128-byte hardware swizzle so
-//     that every consumer thread owns a RUN of 64 contiguous map bytes and still reads it with
-//     conflict-free ld.shared.v4. Bytes in flight are set by the ring, not by registers, and the
+//     SASS UTMALDG.2D; the maps are described as a tensor of 128-byte rows) of 32 KB / G tiles into a
+//     2-stage shared-memory ring with full/empty mbarriers, written with the 128-byte hardware swizzle so
+//     that every consumer thread owns a RUN of 128 contiguous map bytes — one TMA row — and still reads it
+//     with conflict-free ld.shared.v4 (64-byte runs, 16 KB / G tiles and 4 stages where the image rows do
+//     not hold whole 128-byte runs). Bytes in flight are set by the ring, not by registers, and the
 //     producer keeps prefetching the NEXT map while the consumers are in the per-map epilogue
 //     (consumer-only named barrier), so the DRAM pipe never drains;
 //   * arg-max: a packed max.NaN tree per 16-byte chunk (bf16x2 / f16x2 SIMD for 16-bit maps) and ONE
@@ -57,7 +58,7 @@ struct DecodeParams {
   int64_t n_maps;
   int64_t map_bytes;
   int H, W;
-  int rows_per_map;    // streaming kernel: H*W*sizeof / 64 (64-byte runs per map)
+  int rows_per_map;    // streaming kernel: runs (128 or 64 bytes, one per thread and tile) per map
   double scale_x, scale_y;
   float beta_log2e;  // beta * log2(e)
   float skip_delta;  // scalar kernel only: kSoftSkip / beta
@@ -363,12 +364,13 @@ __device__ __forceinline__ void tma_load_rows_after(uint32_t dst_smem, const CUt
 // overlaps the other groups' streaming. Producer warp 8+g (one elected lane) feeds group g.
 // Grid = one resident wave; group (blockIdx.x, g) walks maps blockIdx.x*G + g, +gridDim.x*G, ...
 //
-// Tile = NT/2 rows of 128 bytes, loaded by ONE 2-D TMA tensor copy with the 128-byte swizzle: thread gt owns half
-// (gt & 1) of row gt >> 1, i.e. a RUN of 64 contiguous map bytes (32 bf16 / 16 f32 elements, inside one map row),
-// and reads its four 16-byte chunks at ((4 (gt & 1) + u) ^ ((gt >> 1) & 7)) — conflict-free ld.shared.v4 although
-// the lane stride is 64 bytes. (64-byte TMA rows with the 64-byte swizzle work too but stream 4 % slower.)
-// Owning a contiguous run makes the soft-arg-max bookkeeping per TILE instead of per 16-byte chunk: one
-// (column, row) position, one pair of first-moment FFMA2, one suffix-sum pass over the run.
+// Tile = NT*U/8 rows of 128 bytes, loaded by ONE 2-D TMA tensor copy with the 128-byte swizzle. U = 8: thread gt owns
+// row gt, a RUN of 128 contiguous map bytes (64 bf16 / 32 f32 elements inside one image row), chunk u at u ^ (gt & 7).
+// U = 4: thread gt owns half (gt & 1) of row gt >> 1, a run of 64 bytes, chunk u at (4 (gt & 1) + u) ^ ((gt >> 1) & 7).
+// Either way conflict-free ld.shared.v4 although the lane stride is 128 / 64 bytes. (64-byte TMA rows with the
+// 64-byte swizzle work too but stream 4 % slower.) Owning a contiguous run makes the soft-arg-max bookkeeping per
+// TILE instead of per 16-byte chunk: one (column, row) position, one pair of first-moment FFMA2, one suffix-sum pass
+// over the run — and the longer the run, the less the per-tile fixed costs weigh (launch_persistent).
 #ifndef MVGEO_DEC_MINB
 #define MVGEO_DEC_MINB 2  // measured: 2 CTAs/SM without a register cap beat 3 CTAs/SM at 64 registers (spills)
 #endif
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kDecThreads + producer_threads(G), MVGEO_DEC_M
   extern __shared__ __align__(1024) unsigned char dyn_smem[];  // the 128-byte swizzle pattern repeats every 1024 bytes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rows = p.rows_per_map;                   // 64-byte runs per map
+  const int rows = p.rows_per_map;                   // runs per map
   const int n_full = rows / NT;                      // tiles without padding
   const int n_tiles = (rows + NT - 1) / NT;          // n_full or n_full + 1
   // (A balanced assignment — only ceil(n_maps / rounds) streams active so that no stream walks a ragged last round —

@@ -237,8 +237,8 @@ constexpr float kEpochWindow = 64.0f;  // range only: weights stay below 2^64, s
 constexpr int kFoldPeriod = 16;  // tiles (power of two)
 // Experiment kept for reproduction, OFF: every n-th element pair of a 16-bit run takes its exponential on the FMA
 // pipe (exp2_poly2: 12 instructions per pair instead of 2 MUFU). With the XU pipe 72 % busy and the FMA pipe 25 %
-// this looked like headroom; measured (interleaved A/B, all 20 regimes): n = 4: -6 %, n = 3: -5 %, n = 2: -21 %.
-// The loop is bound by instruction issue, not by the MUFU pipe: every added instruction costs its slot.
+// this looked like headroom; measured (interleaved A/B, all 20 regimes): n = 4: -6 %, n = 3: -5 %, n = 2: -21 %
+// with 64-byte runs, n = 4: -4.4 % with 128-byte runs (XU 77 %). Every added instruction costs its issue slot.
 #ifndef MVGEO_POLY_EVERY
 #define MVGEO_POLY_EVERY 0
 #endif

@@ -12,7 +12,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/ev_bench_
 rm -f $O/ev_regimes.jsonl
 timeout 400 python tools/decode_regimes.py --tag r02 --shapes c2,native32,native16,c5 --out $O/ev_regimes.jsonl > $O/ev_regimes.log 2>&1
 [ -f build/libmvgeo_r01.so ] && timeout 600 python tools/decode_regimes.py --tag r01 --lib build/libmvgeo_r01.so --shapes c2,native32,native16 --iters 3 --out $O/ev_regimes.jsonl >> $O/ev_regimes.log 2>&1
-timeout 300 python tools/shim_latency.py > $O/ev_shim_latency.json 2>> $O/ev_bench_n1.err
+timeout 300 python tools/shim_latency.py > $O/ev_shim_latency.log 2>> $O/ev_bench_n1.err && cp $O/shim_latency.json $O/ev_shim_latency.json
 timeout 300 python examples/ddp_train_step.py --steps 10 --bf16 > $O/ev_c4_n1.json 2>> $O/ev_bench_n1.err; echo "c4 rc=$?"
 # profiler passes
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ev_launches.csv \

@@ -212,10 +212,9 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 }
 
 // ----------------------------------------------------------------------------------------
-// Fast path: 16-byte aligned maps whose size is a multiple of 16 bytes (global soft mode: rows
-// that hold a whole number of 16-byte chunks, so a chunk never straddles two rows).
+// Streaming path: 16-byte aligned maps made of whole 128-byte TMA rows (global soft mode: image rows that hold
+// whole 128- or 64-byte runs, so a thread's run never straddles two image rows).
 // ----------------------------------------------------------------------------------------
-// A "slice" is the U chunks {(t*U + u)*NT + gt, u < U} that one consumer thread owns in tile t.
 
 // Online soft-arg-max state of one thread: sums of w = 2^(h*beta' + nb), nb = -ref*beta', over the
 // elements of the current EPOCH, with coordinates relative to the map centre (exact small floats).
@@ -226,7 +225,8 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // of a warp breaks its record in ~90% of the tiles and the whole warp pays a rescale: 15% of all issued
 // instructions). Floating point keeps its relative precision for weights far from 1, so the reference only
 // moves when a run maximum climbs more than kEpochWindow (log2 units) above it: the first finite run, and
-// the few runs in which a thread climbs the peak. At that moment — and every kFoldPeriod tiles regardless —
+// the few runs in which a thread climbs the peak. At that moment — and every kFoldPeriod 64-byte tiles (half as
+// many 128-byte tiles) regardless —
 // the epoch's f32 sums are folded, in DOUBLE, into the thread's per-map totals in shared memory and start
 // again from zero. The periodic fold bounds what f32 accumulation can lose: once a thread has met the peak
 // its first moments carry the lever arm to the map centre (hundreds of pixels) times the peak's mass, and
@@ -234,7 +234,7 @@ __device__ __forceinline__ void window_accumulate(const DecodeParams& p, const v
 // background holds ~1e-3 of the weight; with at most kFoldPeriod tiles per fold the bound is ~5e-5 px.
 // Cost: nothing per element; ~70 instructions per fold, i.e. ~2% of the loop.
 constexpr float kEpochWindow = 64.0f;  // range only: weights stay below 2^64, sums below 2^100
-constexpr int kFoldPeriod = 16;  // tiles (power of two)
+constexpr int kFoldPeriod = 16;  // tiles of 64-byte runs (power of two)
 // Experiment kept for reproduction, OFF: every n-th element pair of a 16-bit run takes its exponential on the FMA
 // pipe (exp2_poly2: 12 instructions per pair instead of 2 MUFU). With the XU pipe 72 % busy and the FMA pipe 25 %
 // this looked like headroom; measured (interleaved A/B, all 20 regimes): n = 4: -6 %, n = 3: -5 %, n = 2: -21 %
@@ -246,8 +246,8 @@ constexpr int kPolyEvery = MVGEO_POLY_EVERY;
 struct SoftAcc {
   float nb;      // -ref * beta_log2e as rounded (the fold corrects with the SAME value)
   float ref_hi;  // ref + kEpochWindow / beta_log2e
-  f32x2 s, sx, sy;       // sum w, sum w (x0 - ox), sum w (y - oy), x0 = the chunk's first column
-  f32x2 sj;              // sum w i, i = index of the element's 2-element group inside its chunk
+  f32x2 s, sx, sy;       // sum w, sum w (x0 - ox), sum w (y - oy), x0 = the run's first column
+  f32x2 sj;              // sum w i, i = index of the element's 2-element group inside its run
 };
 
 // Per-thread, per-map totals over the finished epochs: S, SX, SY relative to reference nb (32 bytes per thread in
@@ -288,7 +288,7 @@ __device__ __forceinline__ void epoch_fold(SoftAcc& a, uint32_t totals_addr) {
     unpack2(a.sx, h0, h1);
     float j0, j1;
     unpack2(a.sj, j0, j1);
-    // sum_j j*w_j over the chunks = 2 * sum_i i*(w_i.lo + w_i.hi) + sum_i w_i.hi
+    // sum_j j*w_j over the runs = 2 * sum_i i*(w_i.lo + w_i.hi) + sum_i w_i.hi
     const double SX = ((double)h0 + (double)h1) + 2.0 * ((double)j0 + (double)j1) + (double)s_odd;
     unpack2(a.sy, h0, h1);
     const double SY = (double)h0 + (double)h1;

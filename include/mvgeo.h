@@ -103,7 +103,10 @@ int mvgeo_chain_builtin(int robot, mvgeo_chain* out_host);
  * and the inline arg-max loops (DIP_REAL.py:116-124, model/MvRoPose_FR3.py:299-304,
  * model/DREAM_Train.py:371-385,448-460), batched over n_maps = B*V*K maps.
  *
- *   maps      [n_maps, H, W] of `dtype`, base 16-byte aligned for the fast path
+ *   maps      [n_maps, H, W] of `dtype`. Streaming (TMA) kernel: base 16-byte aligned and H*W*sizeof a multiple
+ *             of 128 bytes; global soft mode also needs image rows (W*sizeof) of whole 64-byte runs (whole 128-byte
+ *             runs: the faster instantiation). Any other shape / alignment takes a plain element-wise kernel —
+ *             same results, never an error.
  *   idx       [n_maps] int32   flat arg-max y*W+x; first maximum wins, NaN is maximal
  *                              (torch.argmax semantics)                       (nullable)
  *   peak      [n_maps] f32     the raw maximum                                (nullable)
@@ -291,8 +294,9 @@ int mvgeo_heatmap_mse(const void* pred, int dtype, const float* kp, int64_t n_ma
  * predicted maps, which are read from HBM once (the reference reads them for nn.MSELoss,
  * model/MvRoPose_FR3.py:846-847, and again when decoding for evaluation, :299-304).
  *   kp_target [n_maps, 2] f32 target centres in MAP pixels; partial [n_maps] f32 scratch; loss [1] f32
- * Needs 16-byte aligned maps whose rows hold whole 16-byte chunks and (W + H) * 4 bytes * groups of shared
- * memory <= 16 KB; otherwise MVGEO_EUNSUPPORTED (call the two stand-alone entry points). The gradient pass is
+ * Needs 16-byte aligned maps of whole 128-byte rows (H*W*sizeof % 128 == 0) whose image rows hold whole 64-byte
+ * runs (W*sizeof % 64 == 0) and (W + H) * 4 bytes of shared-memory tables <= 16 KB; otherwise MVGEO_EUNSUPPORTED
+ * (call the two stand-alone entry points). The gradient pass is
  * mvgeo_heatmap_mse with `grad` (it reads the prediction and writes the gradient).
  */
 int mvgeo_decode_mse(const void* maps, int dtype, int64_t n_maps, int H, int W, double scale_x, double scale_y,

@@ -68,11 +68,12 @@ def load_fr3():
 
 
 def load_fr5():
-    """model/Fr5_model_train.ipynb cell 2 (FK + projection) and cell 14 (decoder)."""
+    """model/Fr5_model_train.ipynb cell 2 (FK + projection) and cell 14 (decoder, estimate_camera_pose)."""
     ns = _base_ns()
     exec(_extract_defs(_cell_source("model/Fr5_model_train.ipynb", 2),
                        ["get_dh_matrix", "angle_to_joint_coordinate", "joint_coordinate_to_pixel_plane"]), ns)
-    exec(_extract_defs(_cell_source("model/Fr5_model_train.ipynb", 14), ["extract_keypoints_from_heatmaps"]), ns)
+    exec(_extract_defs(_cell_source("model/Fr5_model_train.ipynb", 14),
+                       ["extract_keypoints_from_heatmaps", "estimate_camera_pose"]), ns)
     return ns
 
 

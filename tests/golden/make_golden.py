@@ -57,7 +57,27 @@ def gen_inputs():
     inp["gt_kp"] = np.array([[40.3, 77.8], [0.0, 0.0], [127.0, 127.0], [-3.5, 60.2], [63.5, 63.5]])
     inp["loss_pred"] = rng.normal(500.0, 100.0, size=(4, 7, 2)).astype(np.float32)
     inp["loss_gt"] = (inp["loss_pred"] + rng.normal(0.0, 5.0, size=(4, 7, 2))).astype(np.float32)
+    # camera-pose case (Fr5, view "top"): joint angles in degrees and the true camera pose; no random draws
+    inp["pose_q"] = np.array([10.0, -80.0, 100.0, -110.0, -85.0, 20.0])
+    inp["pose_rt"] = np.array([[1.9, 0.3, -0.2], [0.1, -0.05, 1.8]])
     return inp
+
+
+POSE_MAP_HW, POSE_IMAGE_HW, POSE_THRESHOLD = (270, 480), (1200, 1920), 0.5
+
+
+def pose_case_maps(uv, low=()):
+    """Belief maps (7, 270, 480) float32 in logit scale for the camera-pose case: a sigma = 2 px blob of amplitude 6 on
+    a -3 floor at every projected key-point uv (image px); key-points in `low` get no blob (score sigmoid(-3) = 0.047,
+    below the 0.5 threshold). Shared by the generator and the tests."""
+    H, W = POSE_MAP_HW
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.empty((len(uv), H, W), dtype=np.float32)
+    for k, (u, v) in enumerate(uv):
+        cx, cy = u * W / POSE_IMAGE_HW[1], v * H / POSE_IMAGE_HW[0]
+        amp = 0.0 if k in low else 6.0
+        m[k] = amp * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * 2.0 ** 2)) - 3.0
+    return m
 
 
 def main():
@@ -160,7 +180,28 @@ def main():
         dict(pred, keypoints_2d=torch.from_numpy(inp["loss_gt"])), gt_keypoints=torch.from_numpy(inp["loss_gt"]),
         lambda_kp=0.0, lambda_fk=2.5)))
 
+    # ---- camera pose without a prior: estimate_camera_pose (FK -> decode -> confidence filter -> cv2.solvePnPRansac EPNP,
+    #      model/Fr5_model_train.ipynb:4707-4753) on belief maps rendered at the projections of the true pose ----
+    import contextlib
+    import io
+
     import cv2
+
+    obj = fr5["angle_to_joint_coordinate"](inp["pose_q"], "top")
+    Kp, dp = out["zedx_K"][0], out["zedx_dist"][0]
+    uv, _ = cv2.projectPoints(obj.astype(np.float64), inp["pose_rt"][0], inp["pose_rt"][1], Kp, dp)
+    uv = uv.reshape(-1, 2)
+    out["pose_uv_true"] = uv
+    for name, low in (("ok", (6,)), ("refused", (1, 3, 5, 6))):
+        cv2.setRNGSeed(7)
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints the scores
+            rvec, tvec, obj3, img2 = fr5["estimate_camera_pose"](
+                torch.tensor(inp["pose_q"]), torch.from_numpy(pose_case_maps(uv, low)), Kp, dp, "top",
+                POSE_IMAGE_HW, POSE_THRESHOLD)
+        out[f"pose_{name}_obj"], out[f"pose_{name}_img"] = obj3, img2
+        out[f"pose_{name}_rt"] = (np.full((2, 3), np.nan) if rvec is None else
+                                  np.stack([np.asarray(rvec).ravel(), np.asarray(tvec).ravel()]))
+
     import scipy
 
     out["versions"] = np.array(f"cv2 {cv2.__version__}; scipy {scipy.__version__}; numpy {np.__version__}; torch {torch.__version__}")

@@ -1247,6 +1247,28 @@ def test_estimate_camera_pose_shims(mv):
     assert fr3.estimate_camera_pose(torch.tensor(ang), hm.cpu(), Kc, dist, "view1", size, 0.5)[0] is None
 
 
+def test_estimate_camera_pose_vs_reference_golden(mv):
+    """compat.fr5.estimate_camera_pose against the UNMODIFIED reference function's outputs (make_golden.py ran
+    model/Fr5_model_train.ipynb:4707-4753 on these belief maps): object points and decoded key-points exactly, the
+    pose up to the estimators' difference (EPnP + RANSAC without refinement vs every-triplet P3P + LM: 1e-2 rad /
+    5 mm between them, both within the 4 px cell quantisation of the true pose), and the same refusal below four
+    confident key-points."""
+    from mvgeo.compat import fr5
+    K, dist = G["zedx_K"][0], G["zedx_dist"][0]
+    for name, low in (("ok", (6,)), ("refused", (1, 3, 5, 6))):
+        maps = torch.from_numpy(_mg.pose_case_maps(G["pose_uv_true"], low))
+        rv, tv, obj, img = fr5.estimate_camera_pose(torch.tensor(INP["pose_q"]), maps, K, dist, "top", _mg.POSE_IMAGE_HW,
+                                                    confidence_threshold=_mg.POSE_THRESHOLD)
+        np.testing.assert_allclose(obj, G[f"pose_{name}_obj"], rtol=0, atol=2e-7)
+        np.testing.assert_array_equal(np.asarray(img, dtype=np.float32), G[f"pose_{name}_img"])
+        ref = G[f"pose_{name}_rt"]
+        if name == "refused":
+            assert rv is None and tv is None and np.isnan(ref).all()
+            continue
+        assert _rot_angle(rv.reshape(3), ref[0]) < 1e-2 and np.abs(tv.reshape(3) - ref[1]).max() < 5e-3
+        assert _rot_angle(rv.reshape(3), INP["pose_rt"][0]) < 2e-2 and np.abs(tv.reshape(3) - INP["pose_rt"][1]).max() < 1e-2
+
+
 @pytest.mark.parametrize("dtype,HW", [(torch.float32, (128, 128)), (torch.bfloat16, (128, 128)), (torch.bfloat16, (240, 320)),
                                       (torch.float16, (120, 160)), (torch.bfloat16, (480, 640))])
 def test_decode_and_mse_one_read(mv, dtype, HW):

@@ -399,3 +399,35 @@ def test_pnp_solve_oracle_p3p_consensus_vs_cv2():
     assert worst_r < 1e-6 and worst_t < 1e-6, (worst_r, worst_t)
     # the reference's refusals: fewer than 4 confident points -> None
     assert O.pnp_solve(X, kp, K, dist, w=np.array([1, 1, 1, 0, 0, 0, 0, 0.0]), min_weight=0.5) is None
+
+
+def test_estimate_camera_pose_golden_from_the_reference():
+    """The reference's own estimate_camera_pose (FK -> sigmoid/arg-max decode -> confidence filter ->
+    cv2.solvePnPRansac EPNP, model/Fr5_model_train.ipynb:4707-4753), run unmodified by make_golden.py on belief maps
+    rendered at the projections of a known camera pose. The oracle must reproduce its intermediate results exactly
+    (FK points, decoded key-points) and its pose up to the estimators' difference: EPnP + RANSAC has no refinement,
+    the oracle ends in an LM optimum; both sit within the 4 px cell quantisation of the true pose, so 1e-2 rad /
+    5 mm between them (measured 3.1e-3 rad / 0.95 mm) and 2e-2 rad / 1 cm to the truth."""
+    q, (rv_true, tv_true) = INP["pose_q"], INP["pose_rt"]
+    K, dist = G["zedx_K"][0], G["zedx_dist"][0]
+    obj = O.fk_fr5(q, "top")
+    np.testing.assert_allclose(obj, G["pose_ok_obj"], rtol=0, atol=6e-8)
+    uv = O.project_points(obj.astype(np.float64), O.rodrigues(rv_true), tv_true, K, dist)
+    np.testing.assert_allclose(uv, G["pose_uv_true"], atol=1e-6)
+    for name, low in (("ok", (6,)), ("refused", (1, 3, 5, 6))):
+        maps = _mg.pose_case_maps(G["pose_uv_true"], low)
+        d = O.decode(maps, _mg.POSE_IMAGE_HW[1] / maps.shape[2], _mg.POSE_IMAGE_HW[0] / maps.shape[1], apply_sigmoid=True)
+        np.testing.assert_array_equal(d["kp_hard"], G[f"pose_{name}_img"])          # bit-exact decode
+        res = O.pnp_solve(obj.astype(np.float64), d["kp_hard"].astype(np.float64), K, dist, w=d["score"],
+                          min_weight=_mg.POSE_THRESHOLD)
+        ref = G[f"pose_{name}_rt"]
+        if name == "refused":
+            assert res is None and np.isnan(ref).all()                              # < 4 confident points: both refuse
+            continue
+        rvec, tvec = res[0], res[1]
+
+        def rot_diff(a, b):
+            return math.acos(min(1.0, max(-1.0, (np.trace(O.rodrigues(a).T @ O.rodrigues(b)) - 1) / 2)))
+        assert rot_diff(rvec, ref[0]) < 1e-2 and np.abs(tvec - ref[1]).max() < 5e-3
+        assert rot_diff(rvec, rv_true) < 2e-2 and np.abs(tvec - tv_true).max() < 1e-2
+        assert rot_diff(ref[0], rv_true) < 2e-2 and np.abs(ref[1] - tv_true).max() < 1e-2
